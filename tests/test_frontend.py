@@ -1,0 +1,77 @@
+"""
+Front-end parity: every array simwave_b200's front end hands to the kernel is
+bit-identical to what the reference front end produced in this environment
+(tests/golden/frontend.npz, made by make_golden.py from /root/reference).
+North-star requirement: "source/receiver grid indices and interpolation
+weights must be bit-exact".
+"""
+import numpy as np
+import pytest
+
+import simwave_b200 as api
+import cases
+
+FIELDS = ["shape", "extended_shape", "nbl", "grid_positions",
+          "adjusted_grid_positions", "points", "values", "offsets",
+          "damping_mask", "coeff2", "coeff1", "dt", "timesteps", "ricker"]
+
+
+@pytest.mark.parametrize("name", sorted(cases.FRONTEND_CASES))
+def test_frontend_tables_bit_exact(golden, name):
+    ref = golden("frontend")
+    out = cases.frontend_outputs(api, cases.FRONTEND_CASES[name])
+    for field in FIELDS:
+        expected = ref["{}/{}".format(name, field)]
+        got = np.asarray(out[field])
+        assert got.dtype == expected.dtype, (field, got.dtype, expected.dtype)
+        assert got.shape == expected.shape, field
+        assert np.array_equal(got, expected), field
+
+
+@pytest.mark.parametrize("space_order", range(2, 21, 2))
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fd_coefficients(golden, space_order, dtype):
+    """Weights vs the reference front end (whose `findiff` dependency is
+    replaced by an independent sympy solve in oracle/ref_stubs)."""
+    ref = golden("frontend")
+    vel = np.full((8, 8), 1500.0, dtype=dtype)
+    sm = api.SpaceModel((0, 70, 0, 70), (10, 10), vel,
+                        space_order=space_order, dtype=dtype)
+    tag = "fd/so{}_{}".format(space_order, np.dtype(dtype).name)
+    for deriv, key in ((2, "_c2"), (1, "_c1")):
+        got = sm.fd_coefficients(deriv)
+        assert got.dtype == dtype
+        assert np.array_equal(got, ref[tag + key])
+
+
+def test_fd_known_values():
+    """Reference tests/test_space_model.py:133-155 (orders 2, 4, 8)."""
+    vel = np.full((8, 8), 1500.0, dtype=np.float32)
+    expect = {
+        2: [-2.0, 1.0],
+        4: [-2.5, 1.33333333e+00, -8.33333333e-02],
+        8: [-2.84722222e+00, 1.60000000e+00, -2.00000000e-01,
+            2.53968254e-02, -1.78571429e-03],
+    }
+    for so, coeffs in expect.items():
+        sm = api.SpaceModel((0, 70, 0, 70), (10, 10), vel, space_order=so)
+        assert np.allclose(sm.fd_coefficients(2), np.float32(coeffs))
+    # appendix B.1 of SURVEY.md: first-derivative weights, order 8
+    sm = api.SpaceModel((0, 70, 0, 70), (10, 10), vel, space_order=8)
+    assert np.allclose(sm.fd_coefficients(1),
+                       np.float32([0, 0.8, -0.2, 0.03809524, -0.0035714286]))
+
+
+def test_kws_full_axis_matches_window():
+    """The windowed evaluation used for the tables agrees bit-for-bit with
+    the full-axis evaluation the reference performs (kws.py:44-135)."""
+    from simwave_b200.kernel.frontend import kws
+    rng = np.random.default_rng(7)
+    for w in range(1, 11):
+        for n in (5, 31, 400):
+            for pos in np.float32(rng.uniform(0, n - 1, size=6)):
+                full = kws.kaiser_windowing_sinc(n, pos, w)
+                b0, e0, v0 = kws.get_kws_valid_points(full)
+                b1, e1, v1 = kws.axis_window(n, pos, w)
+                assert (b0, e0) == (b1, e1)
+                assert np.array_equal(v0, v1)

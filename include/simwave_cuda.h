@@ -1,0 +1,271 @@
+/*
+ * simwave_cuda.h -- C ABI of the B200 (sm_100a) backend for simwave's acoustic
+ * forward-modelling time loop.
+ *
+ * Two layers:
+ *
+ * 1. The drop-in boundary.  Eight shared libraries
+ *        libsimwave_cuda_<2|3>d_<constant|variable>_<f32|f64>.so
+ *    each export ONE symbol, `forward`, with exactly the argument list of the
+ *    reference kernel it replaces, so simwave's Middleware can bind it with the
+ *    argtypes it already builds (simwave/kernel/backend/middleware.py:107-158,
+ *    argument order :166-202, restype c_double :150).  Which variant is used is
+ *    decided by file, as in the reference (middleware.py:26-51).  The shims
+ *    forward to the named entry points below, which live in the core library
+ *    libsimwave_b200.so.
+ *
+ *    Every pointer is a caller-owned host buffer valid for the duration of the
+ *    call; `u` and `receivers` are updated in place; nothing is retained.
+ *    Integers are size_t (ctypes c_size_t), index arrays are size_t* (NumPy
+ *    uint64).  Return value: elapsed wall-clock seconds (>= 0), like the
+ *    reference (constant_density/3d/wave.c:57,658-662).  On failure the
+ *    functions return -1.0 and keep a message retrievable with
+ *    simwave_cuda_last_error(); they never call exit() (the reference CUDA
+ *    path does: constant_density/3d/cuda/wave.cu:13-20) and never throw.
+ *
+ * 2. Side exports (device selection, timing of the last call, a plan API that
+ *    keeps a problem resident on the device so the time loop can be timed
+ *    without host<->device traffic, and the slab-decomposition hooks).
+ *    The `forward` signature is frozen, so every new knob lives here or in
+ *    environment variables:
+ *        SIMWAVE_CUDA_DEVICE   device ordinal used by `forward` (default: current)
+ *        SIMWAVE_CUDA_MATH     strict | fast  (default strict)
+ *        SIMWAVE_CUDA_KERNEL   auto | simple  (auto picks the tiled kernels)
+ *        SIMWAVE_CUDA_DEBUG    1 = synchronise and check after every launch
+ */
+#ifndef SIMWAVE_CUDA_H
+#define SIMWAVE_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------
+ * 1. drop-in entry points (one per reference kernel file x precision)
+ * ---------------------------------------------------------------------- */
+
+/* replaces constant_density/2d/wave.c:23-36 built with -DFLOAT */
+double simwave_cuda_forward_2d_constant_f32(
+    float *u, float *velocity, float *damp,
+    float *wavelet, size_t wavelet_size, size_t wavelet_count,
+    float *coeff, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    float *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    float *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    float *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, float dz, float dx,
+    size_t saving_stride, float dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+/* replaces constant_density/2d/wave.c:23-36 built with -DDOUBLE */
+double simwave_cuda_forward_2d_constant_f64(
+    double *u, double *velocity, double *damp,
+    double *wavelet, size_t wavelet_size, size_t wavelet_count,
+    double *coeff, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    double *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    double *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    double *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, double dz, double dx,
+    size_t saving_stride, double dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+/* replaces constant_density/3d/wave.c:23-36 built with -DFLOAT */
+double simwave_cuda_forward_3d_constant_f32(
+    float *u, float *velocity, float *damp,
+    float *wavelet, size_t wavelet_size, size_t wavelet_count,
+    float *coeff, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    float *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    float *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    float *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, size_t ny, float dz, float dx, float dy,
+    size_t saving_stride, float dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+/* replaces constant_density/3d/wave.c:23-36 built with -DDOUBLE */
+double simwave_cuda_forward_3d_constant_f64(
+    double *u, double *velocity, double *damp,
+    double *wavelet, size_t wavelet_size, size_t wavelet_count,
+    double *coeff, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    double *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    double *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    double *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, size_t ny, double dz, double dx, double dy,
+    size_t saving_stride, double dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+/* replaces variable_density/2d/wave.c:23-36 built with -DFLOAT */
+double simwave_cuda_forward_2d_variable_f32(
+    float *u, float *velocity, float *density, float *damp,
+    float *wavelet, size_t wavelet_size, size_t wavelet_count,
+    float *coeff_order2, float *coeff_order1, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    float *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    float *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    float *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, float dz, float dx,
+    size_t saving_stride, float dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+/* replaces variable_density/2d/wave.c:23-36 built with -DDOUBLE */
+double simwave_cuda_forward_2d_variable_f64(
+    double *u, double *velocity, double *density, double *damp,
+    double *wavelet, size_t wavelet_size, size_t wavelet_count,
+    double *coeff_order2, double *coeff_order1, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    double *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    double *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    double *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, double dz, double dx,
+    size_t saving_stride, double dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+/* replaces variable_density/3d/wave.c:23-36 built with -DFLOAT */
+double simwave_cuda_forward_3d_variable_f32(
+    float *u, float *velocity, float *density, float *damp,
+    float *wavelet, size_t wavelet_size, size_t wavelet_count,
+    float *coeff_order2, float *coeff_order1, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    float *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    float *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    float *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, size_t ny, float dz, float dx, float dy,
+    size_t saving_stride, float dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+/* replaces variable_density/3d/wave.c:23-36 built with -DDOUBLE */
+double simwave_cuda_forward_3d_variable_f64(
+    double *u, double *velocity, double *density, double *damp,
+    double *wavelet, size_t wavelet_size, size_t wavelet_count,
+    double *coeff_order2, double *coeff_order1, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    double *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    double *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    double *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, size_t ny, double dz, double dx, double dy,
+    size_t saving_stride, double dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+/* ------------------------------------------------------------------------
+ * 2. side exports
+ * ---------------------------------------------------------------------- */
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char *simwave_cuda_last_error(void);
+
+/* Library version string, e.g. "simwave_b200 0.1 (sm_100a)". */
+const char *simwave_cuda_version(void);
+
+/* Number of CUDA devices visible (<= 0: none / driver error). */
+int simwave_cuda_device_count(void);
+
+/* Device used by subsequent calls from this thread; -1 restores the default
+ * (SIMWAVE_CUDA_DEVICE, else the current device).  Returns 0 on success. */
+int simwave_cuda_set_device(int device);
+
+/* Timing breakdown of the last successful forward()/plan call on this thread,
+ * in seconds; any pointer may be NULL.
+ *   loop   device time of the time loop alone (CUDA events)
+ *   h2d    uploading and preparing the model and the initial fields
+ *   d2h    draining wavefield slots and receivers after the loop
+ *   total  wall clock of the whole call (what forward() returns)           */
+void simwave_cuda_last_timing(double *loop, double *h2d, double *d2h,
+                              double *total);
+
+/* Number of kernels launched by the last forward()/plan run on this thread. */
+unsigned long long simwave_cuda_last_launch_count(void);
+
+/*
+ * Plan API: a problem kept resident on one device.
+ *
+ * The descriptor carries the same information as the `forward` argument list
+ * (field names follow it); `dtype_bytes` is 4 or 8, `ndim` 2 or 3, `density`
+ * / `coeff_order1` are NULL for constant density.  simwave_plan_create()
+ * uploads everything (model, tables, wavelet, the initial slots of `u`) and
+ * returns NULL on failure.  simwave_plan_run() advances the time loop over
+ * [begin_timestep, end_timestep] exactly as `forward` would and reports the
+ * device time of the loop.  simwave_plan_download() writes the wavefield
+ * slots and receiver rows produced so far into caller buffers laid out like
+ * the `forward` arguments.  A plan belongs to the thread that created it.
+ */
+typedef struct simwave_plan simwave_plan;
+
+typedef struct simwave_problem {
+    int ndim;                 /* 2 or 3                                        */
+    int dtype_bytes;          /* 4 = float, 8 = double                         */
+    void *u;                  /* [num_snapshots][nz][nx]([ny]) in/out          */
+    const void *velocity;     /* [nz][nx]([ny])                                */
+    const void *density;      /* same shape or NULL                            */
+    const void *damp;         /* same shape                                    */
+    const void *wavelet;      /* [wavelet_size][wavelet_count]                 */
+    size_t wavelet_size, wavelet_count;
+    const void *coeff_order2; /* [space_order/2 + 1]                           */
+    const void *coeff_order1; /* same length or NULL                           */
+    const size_t *boundary_conditions;      /* [2*ndim]                       */
+    const size_t *src_points_interval;      /* [num_sources][2*ndim]          */
+    const void *src_points_values;
+    size_t src_points_values_size;
+    const size_t *src_points_values_offset; /* [num_sources+1]                */
+    const size_t *rec_points_interval;
+    const void *rec_points_values;
+    size_t rec_points_values_size;
+    const size_t *rec_points_values_offset;
+    void *receivers;          /* [wavelet_size][num_receivers] in/out          */
+    size_t num_sources, num_receivers;
+    size_t nz, nx, ny;        /* ny ignored in 2D                              */
+    double dz, dx, dy;        /* already rounded to dtype by the caller        */
+    size_t saving_stride;
+    double dt;                /* already rounded to dtype by the caller        */
+    size_t space_order;
+    size_t num_snapshots;
+} simwave_problem;
+
+simwave_plan *simwave_plan_create(const simwave_problem *problem);
+int simwave_plan_run(simwave_plan *plan, size_t begin_timestep,
+                     size_t end_timestep, double *loop_seconds);
+int simwave_plan_download(simwave_plan *plan, void *u, void *receivers);
+/* Reset the wavefield slots to the contents of `u` given at creation (zeros
+ * if that was all zero) so the same plan can be timed repeatedly. */
+int simwave_plan_reset(simwave_plan *plan);
+void simwave_plan_destroy(simwave_plan *plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMWAVE_CUDA_H */

@@ -1,0 +1,767 @@
+// Time-loop engine: uploads a problem, runs the reference's loop structure on
+// the device and drains the results.  See DESIGN.md ("Engine") for the slot
+// model; the short version: the reference keeps all fields in one array
+// u[num_snapshots][cells] and moves three slot indices around it
+// (constant_density/3d/wave.c:47-50,113-124,569-618).  We execute exactly that
+// index logic, but a slot only owns a device buffer while the loop can still
+// touch it; once the indices have moved past a slot its field is drained to
+// the caller's array on a side stream and the buffer is recycled.  Slot
+// identity is preserved, so halo cells (which the reference never clears) see
+// the same history as in the reference.
+#include "sw_engine.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+
+#include "sw_launch.h"
+#include "sw_points.cuh"
+
+namespace sw {
+
+static double wall()
+{
+    using namespace std::chrono;
+    return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+static thread_local Timing g_lastTiming;
+Timing &last_timing() { return g_lastTiming; }
+
+static bool env_is(const char *name, const char *value)
+{
+    const char *v = std::getenv(name);
+    return v && std::strcmp(v, value) == 0;
+}
+
+Options Options::from_env()
+{
+    Options o;
+    o.math = env_is("SIMWAVE_CUDA_MATH", "fast") ? MATH_FAST : MATH_STRICT;
+    o.simple = env_is("SIMWAVE_CUDA_KERNEL", "simple");
+    o.debug = env_is("SIMWAVE_CUDA_DEBUG", "1");
+    o.separateBc = env_is("SIMWAVE_CUDA_BC", "separate");
+    o.device = -1;
+    if (const char *d = std::getenv("SIMWAVE_CUDA_DEVICE"))
+        o.device = std::atoi(d);
+    return o;
+}
+
+void DeviceBuffer::alloc(size_t bytes)
+{
+    release();
+    SW_CUDA(cudaMalloc(&ptr_, bytes ? bytes : 1));
+    bytes_ = bytes;
+}
+
+void DeviceBuffer::release()
+{
+    if (ptr_)
+        cudaFree(ptr_);
+    ptr_ = nullptr;
+    bytes_ = 0;
+}
+
+// ---------------------------------------------------------------------------
+// HostDrain
+// ---------------------------------------------------------------------------
+HostDrain::HostDrain(int device, size_t chunkBytes) : device_(device), chunkBytes_(chunkBytes)
+{
+    SW_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        SW_CUDA(cudaMallocHost(&pinned_[i], chunkBytes_));
+        SW_CUDA(cudaEventCreateWithFlags(&copied_[i], cudaEventDisableTiming));
+    }
+    thread_ = std::thread([this] { worker(); });
+}
+
+HostDrain::~HostDrain()
+{
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    if (thread_.joinable())
+        thread_.join();
+    for (int i = 0; i < 2; i++) {
+        if (pinned_[i]) cudaFreeHost(pinned_[i]);
+        if (copied_[i]) cudaEventDestroy(copied_[i]);
+    }
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+void HostDrain::submit(Job job)
+{
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        queue_.push_back(std::move(job));
+    }
+    cv_.notify_all();
+}
+
+void HostDrain::wait_idle()
+{
+    std::unique_lock<std::mutex> lk(mu_);
+    idle_.wait(lk, [this] { return queue_.empty() && !busy_; });
+    if (!error_.empty()) {
+        std::string e = error_;
+        error_.clear();
+        throw Error("snapshot drain failed: " + e);
+    }
+}
+
+void HostDrain::worker()
+{
+    cudaSetDevice(device_);
+    for (;;) {
+        Job job;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [this] { return stop_ || !queue_.empty(); });
+            if (queue_.empty())
+                return;  // stop requested and nothing left
+            job = std::move(queue_.front());
+            queue_.pop_front();
+            busy_ = true;
+        }
+        try {
+            SW_CUDA(cudaEventSynchronize(job.ready));
+            const size_t rowsPerChunk = std::max<size_t>(1, chunkBytes_ / job.rowBytes);
+            const size_t chunks = (job.rows + rowsPerChunk - 1) / rowsPerChunk;
+            auto issue = [&](size_t c) {
+                const size_t r0 = c * rowsPerChunk;
+                const size_t nr = std::min(rowsPerChunk, job.rows - r0);
+                SW_CUDA(cudaMemcpy2DAsync(pinned_[c & 1], job.rowBytes,
+                                          (const char *)job.src + r0 * job.srcPitchBytes,
+                                          job.srcPitchBytes, job.rowBytes, nr,
+                                          cudaMemcpyDeviceToHost, stream_));
+                SW_CUDA(cudaEventRecord(copied_[c & 1], stream_));
+            };
+            if (chunks)
+                issue(0);
+            for (size_t c = 0; c < chunks; c++) {
+                SW_CUDA(cudaEventSynchronize(copied_[c & 1]));
+                if (c + 1 < chunks)
+                    issue(c + 1);  // overlaps with the memcpy below
+                const size_t r0 = c * rowsPerChunk;
+                const size_t nr = std::min(rowsPerChunk, job.rows - r0);
+                std::memcpy((char *)job.dst + r0 * job.rowBytes, pinned_[c & 1],
+                            nr * job.rowBytes);
+            }
+        } catch (const std::exception &e) {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (error_.empty())
+                error_ = e.what();
+        }
+        if (job.ready)
+            cudaEventDestroy(job.ready);
+        if (job.done)
+            job.done();
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            busy_ = false;
+        }
+        idle_.notify_all();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+
+// true if [p, p+bytes) is all zero bits; scanned by a few threads, stops early
+static bool all_zero(const void *p, size_t bytes)
+{
+    const size_t words = bytes / 8;
+    const uint64_t *w = (const uint64_t *)p;
+    const int nthreads = (bytes > (64u << 20)) ? 8 : 1;
+    std::vector<char> nz(nthreads, 0);
+    auto scan = [&](int t) {
+        const size_t b = words * t / nthreads, e = words * (t + 1) / nthreads;
+        const size_t blk = 4096;
+        for (size_t i = b; i < e; i += blk) {
+            uint64_t acc = 0;
+            const size_t m = std::min(e, i + blk);
+            for (size_t j = i; j < m; j++)
+                acc |= w[j];
+            if (acc) { nz[t] = 1; return; }
+        }
+    };
+    if (nthreads == 1) {
+        scan(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; t++) th.emplace_back(scan, t);
+        for (auto &x : th) x.join();
+    }
+    for (char c : nz)
+        if (c) return false;
+    const unsigned char *tail = (const unsigned char *)p + words * 8;
+    for (size_t i = 0; i < bytes - words * 8; i++)
+        if (tail[i]) return false;
+    return true;
+}
+
+static dim3 row_grid(const Grid &g)
+{
+    const long long rows = (long long)g.nS * g.nM;
+    return dim3((g.nF + 255) / 256, (unsigned)std::min<long long>(rows, 65535), 1);
+}
+
+// ---------------------------------------------------------------------------
+// Plan
+// ---------------------------------------------------------------------------
+template <typename T>
+class Plan : public PlanBase {
+public:
+    Plan(const simwave_problem &pb, const Options &opt);
+    ~Plan() override;
+    void run(size_t begin, size_t end) override;
+    void download(void *u, void *receivers) override;
+    void reset() override;
+
+private:
+    using StepFn = void (*)(int, const StepArgs<T> &, cudaStream_t);
+
+    void check_launch(const char *what);
+    T *field_base(const DeviceBuffer &b) const { return b.as<T>() + guard_ + g_.lpad; }
+    void new_field(DeviceBuffer &b);
+    T *acquire();
+    void give_back(T *buf);
+    void ensure_live(size_t slot);
+    void retire(size_t slot, bool keep);
+    void retire_below(size_t bound);
+    void upload_dense(const T *host, T *pitchedBase);
+    void launch_step(const StepArgs<T> &a);
+    void launch_sources(const StepArgs<T> &a, size_t n);
+    void launch_receivers(const T *cur, size_t n);
+    void launch_boundaries(T *next);
+
+    Options opt_;
+    int device_ = 0;
+    int ndim_;
+    bool varden_;
+    Grid g_;
+    size_t guard_;          // elements before/after each field allocation
+    size_t denseCells_;
+    size_t fieldBytes_;
+
+    T *hostU_;
+    T *hostRec_;
+    size_t numSlots_, stride_, waveletSize_, waveletCount_, nsrc_, nrec_;
+    std::vector<char> slotZero_;
+
+    DeviceBuffer c0_, q_, rho_, stage_;
+    DeviceBuffer wavelet_, srcIv_, srcVal_, srcOff_, recIv_, recVal_, recOff_, recOut_;
+    StepArgs<T> args_;
+    PointTables<T> srcTab_, recTab_;
+    int srcMode_ = SRC_DISJOINT;
+    int srcMaxPoints_ = 1;
+    StepFn stepSimple_ = nullptr;
+
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t evBegin_ = nullptr, evEnd_ = nullptr;
+
+    // slots
+    std::map<size_t, T *> live_;
+    std::map<size_t, bool> dirty_;
+    std::vector<std::unique_ptr<DeviceBuffer>> buffers_;
+    std::vector<T *> free_;
+    std::mutex poolMu_;
+    std::condition_variable poolCv_;
+    size_t maxBuffers_ = 6;
+    size_t prevT_ = 0, curT_ = 1, nextT_ = 2;
+    size_t recBegin_ = 0, recEnd_ = 0;   // receiver rows produced so far [begin,end)
+
+    std::unique_ptr<HostDrain> drain_;
+};
+
+template <typename T>
+void Plan<T>::check_launch(const char *what)
+{
+    timing.launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && opt_.debug)
+        e = cudaStreamSynchronize(stream_);
+    if (e != cudaSuccess)
+        throw Error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+template <typename T>
+Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
+{
+    const double t0 = wall();
+    ndim_ = pb.ndim;
+    varden_ = pb.density != nullptr;
+    if (ndim_ != 2 && ndim_ != 3)
+        throw Error("ndim must be 2 or 3");
+    if (pb.space_order < 2 || pb.space_order > 2 * kMaxRadius || pb.space_order % 2)
+        throw Error("space_order must be even and between 2 and 20");
+    if (varden_ && !pb.coeff_order1)
+        throw Error("variable density needs coeff_order1");
+
+    if (opt_.device >= 0)
+        SW_CUDA(cudaSetDevice(opt_.device));
+    SW_CUDA(cudaGetDevice(&device_));
+
+    const int r = (int)(pb.space_order / 2);
+    Grid &g = g_;
+    g.ndim = ndim_;
+    if (ndim_ == 3) {
+        g.nS = (int)pb.nz; g.nM = (int)pb.nx; g.nF = (int)pb.ny;
+    } else {
+        g.nS = 1; g.nM = (int)pb.nz; g.nF = (int)pb.nx;
+    }
+    g.r = r;
+    if (g.nF < 2 * r + 1 || g.nM < 2 * r + 1 || (ndim_ == 3 && g.nS < 2 * r + 1))
+        throw Error("grid smaller than the stencil halo");
+    const int align = 128 / (int)sizeof(T);
+    g.lpad = (align - r % align) % align;
+    g.pitch = ((long long)g.lpad + g.nF + align - 1) / align * align;
+    g.planeStride = (long long)g.nM * g.pitch;
+    g.cells = (long long)g.nS * g.planeStride;
+    guard_ = 2 * align;
+    denseCells_ = (size_t)g.nS * g.nM * g.nF;
+    fieldBytes_ = (g.cells + 2 * guard_) * sizeof(T);
+
+    hostU_ = (T *)pb.u;
+    hostRec_ = (T *)pb.receivers;
+    numSlots_ = pb.num_snapshots;
+    stride_ = pb.saving_stride;
+    waveletSize_ = pb.wavelet_size;
+    waveletCount_ = pb.wavelet_count ? pb.wavelet_count : 1;
+    nsrc_ = pb.num_sources;
+    nrec_ = pb.num_receivers;
+    if (numSlots_ < 3)
+        throw Error("u must hold at least 3 slots");
+
+    SW_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    SW_CUDA(cudaEventCreate(&evBegin_));
+    SW_CUDA(cudaEventCreate(&evEnd_));
+
+    // ---- static part of the step arguments ------------------------------
+    StepArgs<T> &a = args_;
+    std::memset(&a, 0, sizeof(a));
+    a.g = g;
+    const T *c2 = (const T *)pb.coeff_order2;
+    const T *c1 = (const T *)pb.coeff_order1;
+    for (int i = 0; i <= r; i++) {
+        a.c2[i] = c2[i];
+        a.c1[i] = c1 ? c1[i] : T(0);
+    }
+    // spacing per axis in (S,M,F) order; squares rounded in T like the
+    // reference's `f_type dzSquared = dz * dz`
+    T h[3];
+    if (ndim_ == 3) { h[0] = (T)pb.dz; h[1] = (T)pb.dx; h[2] = (T)pb.dy; }
+    else            { h[0] = T(1);     h[1] = (T)pb.dz; h[2] = (T)pb.dx; }
+    for (int i = 0; i < 3; i++) {
+        volatile T sq = h[i] * h[i];
+        a.h2[i] = sq;
+        a.inv_h2[i] = T(1) / a.h2[i];
+        volatile T f4 = T(4) * a.h2[i];
+        a.four_h2[i] = f4;
+    }
+    const size_t *bc = pb.boundary_conditions;
+    if (ndim_ == 3) {
+        for (int i = 0; i < 6; i++) a.bc[i] = (int)bc[i];
+    } else {
+        a.bc[0] = a.bc[1] = 0;
+        for (int i = 0; i < 4; i++) a.bc[2 + i] = (int)bc[i];
+    }
+    for (int i = 0; i < 6; i++)
+        if (a.bc[i] < 0 || a.bc[i] > 2)
+            throw Error("boundary condition codes must be 0, 1 or 2");
+    a.quirk = (ndim_ == 3 && varden_ && pb.nx != pb.ny) ? 1 : 0;
+    a.denseNx = (int)pb.nx;
+    a.denseNy = (int)(ndim_ == 3 ? pb.ny : 1);
+    const int need = 3 * r + 2;
+    const bool roomy = g.nF >= need && g.nM >= need && (ndim_ == 2 || g.nS >= need);
+    a.fuse_bc = (roomy && !opt_.separateBc) ? 1 : 0;
+
+    // ---- model: c0, q (and density) in pitched layout ----------------------
+    const T dt = (T)pb.dt;
+    volatile T dtsqv = dt * dt;   // rounded in T, like `f_type dtSquared = dt * dt`
+    const T dtsq = dtsqv;
+
+    new_field(c0_);
+    new_field(q_);
+    stage_.alloc(2 * denseCells_ * sizeof(T));
+    T *stageA = stage_.as<T>(), *stageB = stage_.as<T>() + denseCells_;
+    SW_CUDA(cudaMemcpyAsync(stageA, pb.velocity, denseCells_ * sizeof(T),
+                            cudaMemcpyHostToDevice, stream_));
+    SW_CUDA(cudaMemcpyAsync(stageB, pb.damp, denseCells_ * sizeof(T),
+                            cudaMemcpyHostToDevice, stream_));
+    model_kernel<T><<<row_grid(g), 256, 0, stream_>>>(g, stageA, stageB, dt, dtsq,
+                                                      field_base(c0_), field_base(q_));
+    check_launch("model_kernel");
+    if (varden_) {
+        new_field(rho_);
+        upload_dense((const T *)pb.density, field_base(rho_));
+    }
+    a.c0 = field_base(c0_);
+    a.q = field_base(q_);
+    a.rho = varden_ ? field_base(rho_) : nullptr;
+
+    // ---- wavelet and tables -------------------------------------------------
+    auto to_device = [&](DeviceBuffer &b, const void *src, size_t bytes) {
+        b.alloc(bytes);
+        if (bytes)
+            SW_CUDA(cudaMemcpyAsync(b.get(), src, bytes, cudaMemcpyHostToDevice, stream_));
+    };
+    to_device(wavelet_, pb.wavelet, waveletSize_ * waveletCount_ * sizeof(T));
+    to_device(srcIv_, pb.src_points_interval, nsrc_ * 2 * ndim_ * sizeof(size_t));
+    to_device(srcVal_, pb.src_points_values, pb.src_points_values_size * sizeof(T));
+    to_device(srcOff_, pb.src_points_values_offset, (nsrc_ + 1) * sizeof(size_t));
+    to_device(recIv_, pb.rec_points_interval, nrec_ * 2 * ndim_ * sizeof(size_t));
+    to_device(recVal_, pb.rec_points_values, pb.rec_points_values_size * sizeof(T));
+    to_device(recOff_, pb.rec_points_values_offset, (nrec_ + 1) * sizeof(size_t));
+    recOut_.alloc(std::max<size_t>(1, waveletSize_ * nrec_) * sizeof(T));
+    SW_CUDA(cudaMemsetAsync(recOut_.get(), 0, recOut_.bytes(), stream_));
+    srcTab_ = {srcIv_.as<unsigned long long>(), srcVal_.as<T>(),
+               srcOff_.as<unsigned long long>(), (int)nsrc_};
+    recTab_ = {recIv_.as<unsigned long long>(), recVal_.as<T>(),
+               recOff_.as<unsigned long long>(), (int)nrec_};
+
+    // validate windows and classify source overlap
+    auto check_windows = [&](const size_t *iv, size_t count, const char *what) {
+        const int ext[3] = {g.nS, g.nM, g.nF};
+        for (size_t i = 0; i < count; i++)
+            for (int ax = 0; ax < ndim_; ax++) {
+                const size_t lo = iv[(i * ndim_ + ax) * 2], hi = iv[(i * ndim_ + ax) * 2 + 1];
+                if (lo > hi || hi >= (size_t)ext[ax + 3 - ndim_])
+                    throw Error(std::string(what) + " window outside the grid");
+                if (ax == ndim_ - 1 && hi - lo + 1 > 32)
+                    throw Error(std::string(what) + " window wider than 32 points");
+            }
+    };
+    check_windows(pb.src_points_interval, nsrc_, "source");
+    check_windows(pb.rec_points_interval, nrec_, "receiver");
+    {
+        const size_t *iv = pb.src_points_interval;
+        bool overlap = false;
+        srcMaxPoints_ = 1;
+        for (size_t i = 0; i < nsrc_; i++) {
+            int pts = 1;
+            for (int ax = 0; ax < ndim_; ax++)
+                pts *= (int)(iv[(i * ndim_ + ax) * 2 + 1] - iv[(i * ndim_ + ax) * 2] + 1);
+            srcMaxPoints_ = std::max(srcMaxPoints_, pts);
+        }
+        if (nsrc_ > 4096) {
+            overlap = true;
+        } else {
+            for (size_t i = 0; i < nsrc_ && !overlap; i++)
+                for (size_t j = i + 1; j < nsrc_ && !overlap; j++) {
+                    bool hit = true;
+                    for (int ax = 0; ax < ndim_; ax++) {
+                        const size_t li = iv[(i * ndim_ + ax) * 2], hi_ = iv[(i * ndim_ + ax) * 2 + 1];
+                        const size_t lj = iv[(j * ndim_ + ax) * 2], hj = iv[(j * ndim_ + ax) * 2 + 1];
+                        hit = hit && li <= hj && lj <= hi_;
+                    }
+                    overlap = hit;
+                }
+        }
+        srcMode_ = !overlap ? SRC_DISJOINT : (nsrc_ <= 64 ? SRC_ORDERED : SRC_ATOMIC);
+    }
+
+    // ---- kernels ---------------------------------------------------------------
+    if (ndim_ == 3)
+        stepSimple_ = varden_ ? &launch_step_simple<T, 3, true> : &launch_step_simple<T, 3, false>;
+    else
+        stepSimple_ = varden_ ? &launch_step_simple<T, 2, true> : &launch_step_simple<T, 2, false>;
+
+    // ---- which of the caller's slots start as zeros ----------------------------
+    slotZero_.assign(numSlots_, 0);
+    if (all_zero(hostU_, numSlots_ * denseCells_ * sizeof(T))) {
+        std::fill(slotZero_.begin(), slotZero_.end(), 1);
+    } else {
+        for (size_t s = 0; s < numSlots_; s++)
+            slotZero_[s] = all_zero(hostU_ + s * denseCells_, denseCells_ * sizeof(T));
+    }
+
+    drain_.reset(new HostDrain(device_, 32u << 20));
+    SW_CUDA(cudaStreamSynchronize(stream_));
+    timing.h2d = wall() - t0;
+}
+
+template <typename T>
+Plan<T>::~Plan()
+{
+    drain_.reset();   // joins the worker before buffers go away
+    if (stream_) {
+        cudaStreamSynchronize(stream_);
+        cudaStreamDestroy(stream_);
+    }
+    if (evBegin_) cudaEventDestroy(evBegin_);
+    if (evEnd_) cudaEventDestroy(evEnd_);
+}
+
+template <typename T>
+void Plan<T>::new_field(DeviceBuffer &b)
+{
+    b.alloc(fieldBytes_);
+    SW_CUDA(cudaMemsetAsync(b.get(), 0, fieldBytes_, stream_));
+}
+
+template <typename T>
+void Plan<T>::upload_dense(const T *host, T *pitchedBase)
+{
+    if (!stage_.get())
+        stage_.alloc(2 * denseCells_ * sizeof(T));
+    SW_CUDA(cudaMemcpyAsync(stage_.get(), host, denseCells_ * sizeof(T),
+                            cudaMemcpyHostToDevice, stream_));
+    pack_kernel<T><<<row_grid(g_), 256, 0, stream_>>>(g_, stage_.as<T>(), pitchedBase);
+    check_launch("pack_kernel");
+}
+
+template <typename T>
+T *Plan<T>::acquire()
+{
+    std::unique_lock<std::mutex> lk(poolMu_);
+    if (free_.empty() && buffers_.size() < maxBuffers_) {
+        lk.unlock();
+        std::unique_ptr<DeviceBuffer> b(new DeviceBuffer());
+        new_field(*b);
+        T *base = field_base(*b);
+        buffers_.push_back(std::move(b));
+        return base;
+    }
+    poolCv_.wait(lk, [this] { return !free_.empty(); });
+    T *base = free_.back();
+    free_.pop_back();
+    return base;
+}
+
+template <typename T>
+void Plan<T>::give_back(T *buf)
+{
+    {
+        std::lock_guard<std::mutex> lk(poolMu_);
+        free_.push_back(buf);
+    }
+    poolCv_.notify_all();
+}
+
+template <typename T>
+void Plan<T>::ensure_live(size_t slot)
+{
+    if (live_.count(slot))
+        return;
+    if (slot >= numSlots_)
+        throw Error("time loop would touch slot " + std::to_string(slot) + " but u has only " +
+                    std::to_string(numSlots_) + " slots");
+    T *buf = acquire();
+    // whole allocation (guards and row padding included) starts from zero
+    SW_CUDA(cudaMemsetAsync((char *)(buf - g_.lpad - guard_), 0, fieldBytes_, stream_));
+    if (!slotZero_[slot])
+        upload_dense(hostU_ + slot * denseCells_, buf);
+    live_[slot] = buf;
+    dirty_[slot] = false;
+}
+
+// Slot leaves the device: drained to the caller's array if it was written.
+// keep == true leaves the slot live (plan download).
+template <typename T>
+void Plan<T>::retire(size_t slot, bool keep)
+{
+    T *buf = live_.at(slot);
+    const bool dirty = dirty_[slot];
+    if (!keep) {
+        live_.erase(slot);
+        dirty_.erase(slot);
+    }
+    if (!dirty) {
+        if (!keep)
+            give_back(buf);
+        return;
+    }
+    HostDrain::Job job;
+    job.src = buf;
+    job.dst = hostU_ + slot * denseCells_;
+    job.rowBytes = (size_t)g_.nF * sizeof(T);
+    job.srcPitchBytes = (size_t)g_.pitch * sizeof(T);
+    job.rows = (size_t)g_.nS * g_.nM;
+    SW_CUDA(cudaEventCreateWithFlags(&job.ready, cudaEventDisableTiming));
+    SW_CUDA(cudaEventRecord(job.ready, stream_));
+    if (!keep)
+        job.done = [this, buf] { give_back(buf); };
+    drain_->submit(std::move(job));
+}
+
+template <typename T>
+void Plan<T>::retire_below(size_t bound)
+{
+    while (!live_.empty() && live_.begin()->first < bound)
+        retire(live_.begin()->first, false);
+}
+
+template <typename T>
+void Plan<T>::launch_step(const StepArgs<T> &a)
+{
+    stepSimple_(opt_.math, a, stream_);
+    check_launch("step kernel");
+}
+
+template <typename T>
+void Plan<T>::launch_sources(const StepArgs<T> &a, size_t n)
+{
+    if (!nsrc_)
+        return;
+    dim3 grid((srcMaxPoints_ + 127) / 128, (unsigned)std::min<size_t>(nsrc_, 65535), 1);
+    if (ndim_ == 3)
+        source_kernel<T, 3><<<grid, 128, 0, stream_>>>(a, srcTab_, wavelet_.as<T>(),
+                                                       (int)waveletCount_, (long long)n, srcMode_);
+    else
+        source_kernel<T, 2><<<grid, 128, 0, stream_>>>(a, srcTab_, wavelet_.as<T>(),
+                                                       (int)waveletCount_, (long long)n, srcMode_);
+    check_launch("source_kernel");
+}
+
+template <typename T>
+void Plan<T>::launch_receivers(const T *cur, size_t n)
+{
+    if (!nrec_)
+        return;
+    T *row = recOut_.as<T>() + (n - 1) * nrec_;
+    const unsigned blocks = (unsigned)((nrec_ * 32 + 127) / 128);
+    if (ndim_ == 3)
+        receiver_kernel<T, 3><<<blocks, 128, 0, stream_>>>(g_, cur, recTab_, row);
+    else
+        receiver_kernel<T, 2><<<blocks, 128, 0, stream_>>>(g_, cur, recTab_, row);
+    check_launch("receiver_kernel");
+}
+
+template <typename T>
+void Plan<T>::launch_boundaries(T *next)
+{
+    // F, then M, then S (3d/wave.c:311-480; 2d/wave.c:285-393)
+    const int n[3] = {g_.nS, g_.nM, g_.nF};
+    for (int axis = AX_F; axis >= (ndim_ == 3 ? AX_S : AX_M); axis--) {
+        const int before = args_.bc[2 * axis], after = args_.bc[2 * axis + 1];
+        if (!before && !after)
+            continue;
+        long long lines = 1;
+        for (int ax = (ndim_ == 3 ? AX_S : AX_M); ax <= AX_F; ax++)
+            if (ax != axis)
+                lines *= n[ax] - 2 * g_.r;
+        boundary_axis_kernel<T><<<(unsigned)((lines + 127) / 128), 128, 0, stream_>>>(
+            g_, next, axis, before, after);
+        check_launch("boundary_axis_kernel");
+    }
+}
+
+template <typename T>
+void Plan<T>::run(size_t begin, size_t end)
+{
+    if (begin < 1 || end > waveletSize_)
+        throw Error("timestep range outside [1, wavelet_size]");
+    const double t0 = wall();
+    SW_CUDA(cudaEventRecord(evBegin_, stream_));
+    if (recBegin_ == recEnd_) { recBegin_ = begin - 1; recEnd_ = begin - 1; }
+
+    for (size_t n = begin; n <= end; n++) {
+        // slot indices, as constant_density/3d/wave.c:113-124
+        if (stride_ == 0) {
+            prevT_ = (n - 1) % 3; curT_ = n % 3; nextT_ = (n + 1) % 3;
+        } else if (stride_ == 1) {
+            prevT_ = n - 1; curT_ = n; nextT_ = n + 1;
+        }
+        if (stride_ != 0)
+            retire_below(std::min(prevT_, std::min(curT_, nextT_)));
+        ensure_live(prevT_);
+        ensure_live(curT_);
+        ensure_live(nextT_);
+
+        StepArgs<T> a = args_;
+        a.prev = live_[prevT_];
+        a.cur = live_[curT_];
+        a.next = live_[nextT_];
+
+        launch_receivers(a.cur, n);
+        launch_step(a);
+        launch_sources(a, n);
+        if (!a.fuse_bc)
+            launch_boundaries(a.next);
+        dirty_[nextT_] = true;
+
+        // slot bookkeeping for saving_stride > 1, as 3d/wave.c:569-618
+        if (stride_ > 1) {
+            if (n % stride_ == 1) {
+                prevT_ = curT_;
+                curT_ += 1;
+                nextT_ += 1;
+                if (stride_ % 2 == 0 && n < end) {
+                    std::swap(curT_, nextT_);
+                    // the reference exchanges the two slots' contents; here
+                    // the slots exchange their buffers
+                    ensure_live(curT_);
+                    ensure_live(nextT_);
+                    std::swap(live_[curT_], live_[nextT_]);
+                    dirty_[curT_] = dirty_[nextT_] = true;
+                }
+            } else {
+                prevT_ = curT_;
+                curT_ = nextT_;
+                nextT_ = prevT_;
+            }
+        }
+    }
+    recEnd_ = std::max(recEnd_, end);
+    SW_CUDA(cudaEventRecord(evEnd_, stream_));
+    SW_CUDA(cudaEventSynchronize(evEnd_));
+    float ms = 0;
+    SW_CUDA(cudaEventElapsedTime(&ms, evBegin_, evEnd_));
+    timing.loop = ms * 1e-3;
+    (void)t0;
+}
+
+template <typename T>
+void Plan<T>::download(void *u, void *receivers)
+{
+    const double t0 = wall();
+    T *saveU = hostU_;
+    if (u)
+        hostU_ = (T *)u;
+    std::vector<size_t> slots;
+    for (auto &kv : live_)
+        slots.push_back(kv.first);
+    for (size_t s : slots)
+        retire(s, true);
+    drain_->wait_idle();
+    hostU_ = saveU;
+    T *rec = receivers ? (T *)receivers : hostRec_;
+    if (rec && nrec_ && recEnd_ > recBegin_) {
+        SW_CUDA(cudaMemcpyAsync(rec + recBegin_ * nrec_, recOut_.as<T>() + recBegin_ * nrec_,
+                                (recEnd_ - recBegin_) * nrec_ * sizeof(T),
+                                cudaMemcpyDeviceToHost, stream_));
+        SW_CUDA(cudaStreamSynchronize(stream_));
+    }
+    timing.d2h = wall() - t0;
+}
+
+template <typename T>
+void Plan<T>::reset()
+{
+    drain_->wait_idle();
+    SW_CUDA(cudaStreamSynchronize(stream_));
+    for (auto &kv : live_)
+        give_back(kv.second);
+    live_.clear();
+    dirty_.clear();
+    prevT_ = 0; curT_ = 1; nextT_ = 2;
+    recBegin_ = recEnd_ = 0;
+    SW_CUDA(cudaMemsetAsync(recOut_.get(), 0, recOut_.bytes(), stream_));
+    timing.launches = 0;
+}
+
+std::unique_ptr<PlanBase> make_plan(const simwave_problem &pb, const Options &opt)
+{
+    if (pb.dtype_bytes == 4)
+        return std::unique_ptr<PlanBase>(new Plan<float>(pb, opt));
+    if (pb.dtype_bytes == 8)
+        return std::unique_ptr<PlanBase>(new Plan<double>(pb, opt));
+    throw Error("dtype_bytes must be 4 or 8");
+}
+
+}  // namespace sw

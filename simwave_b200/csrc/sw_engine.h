@@ -1,0 +1,105 @@
+// Time-loop engine: a problem resident on one device.
+#pragma once
+
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/simwave_cuda.h"
+#include "sw_common.h"
+
+namespace sw {
+
+struct Options {
+    int math;          // MATH_STRICT / MATH_FAST
+    bool simple;       // force the plain kernels
+    bool debug;        // synchronise + check after every launch
+    bool separateBc;   // stand-alone boundary kernels instead of the fused form
+    int device;        // -1: current
+    static Options from_env();
+};
+
+struct Timing {
+    double loop = 0, h2d = 0, d2h = 0, total = 0;
+    unsigned long long launches = 0;
+};
+
+// RAII device allocation
+class DeviceBuffer {
+public:
+    DeviceBuffer() = default;
+    explicit DeviceBuffer(size_t bytes) { alloc(bytes); }
+    ~DeviceBuffer() { release(); }
+    DeviceBuffer(const DeviceBuffer &) = delete;
+    DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+    DeviceBuffer(DeviceBuffer &&o) noexcept : ptr_(o.ptr_), bytes_(o.bytes_) { o.ptr_ = nullptr; o.bytes_ = 0; }
+    DeviceBuffer &operator=(DeviceBuffer &&o) noexcept
+    {
+        if (this != &o) { release(); ptr_ = o.ptr_; bytes_ = o.bytes_; o.ptr_ = nullptr; o.bytes_ = 0; }
+        return *this;
+    }
+    void alloc(size_t bytes);
+    void release();
+    void *get() const { return ptr_; }
+    template <typename U> U *as() const { return static_cast<U *>(ptr_); }
+    size_t bytes() const { return bytes_; }
+
+private:
+    void *ptr_ = nullptr;
+    size_t bytes_ = 0;
+};
+
+// Drains pitched device fields into dense caller memory on a side stream:
+// device -> pinned staging (cudaMemcpy2DAsync, double buffered) -> memcpy into
+// the (pageable) destination, all on a worker thread so the launch thread
+// keeps queueing time steps.  This is how saving_stride snapshots and the
+// final slots leave the device.
+class HostDrain {
+public:
+    struct Job {
+        const void *src;        // device, pitched, element (0,0,0)
+        void *dst;              // host, dense
+        size_t rowBytes;        // nF * sizeof(T)
+        size_t srcPitchBytes;
+        size_t rows;            // nS * nM
+        cudaEvent_t ready;      // recorded on the compute stream (owned by the job)
+        std::function<void()> done;
+    };
+    HostDrain(int device, size_t chunkBytes);
+    ~HostDrain();
+    void submit(Job job);
+    void wait_idle();           // rethrows a worker failure
+private:
+    void worker();
+    int device_;
+    size_t chunkBytes_;
+    void *pinned_[2] = {nullptr, nullptr};
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t copied_[2] = {nullptr, nullptr};
+    std::thread thread_;
+    std::mutex mu_;
+    std::condition_variable cv_, idle_;
+    std::deque<Job> queue_;
+    bool busy_ = false, stop_ = false;
+    std::string error_;
+};
+
+class PlanBase {
+public:
+    virtual ~PlanBase() {}
+    virtual void run(size_t begin, size_t end) = 0;
+    virtual void download(void *u, void *receivers) = 0;
+    virtual void reset() = 0;
+    Timing timing;
+};
+
+std::unique_ptr<PlanBase> make_plan(const simwave_problem &pb, const Options &opt);
+
+Timing &last_timing();
+
+}  // namespace sw

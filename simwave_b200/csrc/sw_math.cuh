@@ -1,0 +1,151 @@
+// Arithmetic of one grid-point update, written once for every kernel.
+//
+// The reference kernel is C99 compiled without contraction; parts of its
+// update are promoted to double by double literals (constant_density/3d/
+// wave.c:177-185).  Two math modes are offered:
+//
+//   STRICT  every operation is rounded exactly where the reference rounds it
+//           (no FMA contraction, true divisions, the same float/double mix).
+//           With identical inputs the result is bit-identical to the
+//           reference's sequential C kernel.
+//   FAST    the Laplacian uses FMA and multiplies by the rounded reciprocal of
+//           h^2; the leapfrog combination keeps the reference's double
+//           accumulation, so only the small `value` term can differ in its
+//           last bit.
+#pragma once
+
+#include "sw_common.h"
+
+namespace sw {
+
+enum MathMode { MATH_FAST = 0, MATH_STRICT = 1 };
+
+template <typename T>
+struct Ops;
+
+template <>
+struct Ops<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
+};
+
+template <>
+struct Ops<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
+};
+
+// acc + c * (a + b)     -- one ring of a second-derivative stencil
+template <typename T, int MATH>
+__device__ __forceinline__ T ring_sum(T acc, T c, T a, T b)
+{
+    if (MATH == MATH_STRICT)
+        return Ops<T>::add(acc, Ops<T>::mul(c, Ops<T>::add(a, b)));
+    return Ops<T>::fma(c, a + b, acc);
+}
+
+// acc + c * (a - b)     -- one ring of a first-derivative stencil
+template <typename T, int MATH>
+__device__ __forceinline__ T ring_diff(T acc, T c, T a, T b)
+{
+    if (MATH == MATH_STRICT)
+        return Ops<T>::add(acc, Ops<T>::mul(c, Ops<T>::sub(a, b)));
+    return Ops<T>::fma(c, a - b, acc);
+}
+
+// x / h2
+template <typename T, int MATH>
+__device__ __forceinline__ T over_h2(T x, T h2, T inv_h2)
+{
+    if (MATH == MATH_STRICT)
+        return Ops<T>::div(x, h2);
+    return Ops<T>::mul(x, inv_h2);
+}
+
+// sum of the per-axis second derivatives, F first, S last
+// (3d/wave.c:174: sum_y/dy2 + sum_x/dx2 + sum_z/dz2; 2d/wave.c:167)
+template <typename T, int NDIM, int MATH>
+__device__ __forceinline__ T laplacian(T sdS, T sdM, T sdF, const T *h2, const T *inv_h2)
+{
+    T v = Ops<T>::add(over_h2<T, MATH>(sdF, h2[AX_F], inv_h2[AX_F]),
+                      over_h2<T, MATH>(sdM, h2[AX_M], inv_h2[AX_M]));
+    if (NDIM == 3)
+        v = Ops<T>::add(v, over_h2<T, MATH>(sdS, h2[AX_S], inv_h2[AX_S]));
+    // the reference starts from `value = 0.0; value += ...`
+    return Ops<T>::add(T(0), v);
+}
+
+// variable-density correction: value -= (tF + tM + tS) / rho
+// with t = (fd_p * fd_rho) / (4 * h2)   (variable_density/3d/wave.c:196-200)
+template <typename T, int NDIM>
+__device__ __forceinline__ T density_term(T value, T fpS, T frS, T fpM, T frM, T fpF, T frF,
+                                          const T *four_h2, T rho)
+{
+    T tF = Ops<T>::div(Ops<T>::mul(fpF, frF), four_h2[AX_F]);
+    T tM = Ops<T>::div(Ops<T>::mul(fpM, frM), four_h2[AX_M]);
+    T t = Ops<T>::add(tF, tM);
+    if (NDIM == 3) {
+        T tS = Ops<T>::div(Ops<T>::mul(fpS, frS), four_h2[AX_S]);
+        t = Ops<T>::add(t, tS);
+    }
+    return Ops<T>::sub(value, Ops<T>::div(t, rho));
+}
+
+// Damping factors of a point inside an absorbing layer (q != 0):
+//   D = 1.0 + q, N = 1.0 - q, the literal 1.0 making the add a double add
+//   (3d/wave.c:180-181).
+template <typename T>
+__device__ __forceinline__ void damping_factors(T q, T &D, T &N)
+{
+    D = (T)__dadd_rn(1.0, (double)q);
+    N = (T)__dsub_rn(1.0, (double)q);
+}
+
+// u_next = 2.0/D * u - (N/D) * u_prev + value * (c0/D)        (3d/wave.c:183-185)
+// `lap` is the spatial operator before the dt^2 v^2 scaling.
+template <typename T>
+__device__ __forceinline__ T leapfrog(T lap, T u, T prev, T c0, T q)
+{
+    if (q == T(0)) {
+        // D == N == 1: 2.0/D*u and (N/D)*prev are exact, value = lap*c0
+        T value = Ops<T>::mul(lap, c0);
+        double d = __dsub_rn((double)Ops<T>::mul(T(2), u), (double)prev);
+        return (T)__dadd_rn(d, (double)value);
+    }
+    T D, N;
+    damping_factors(q, D, N);
+    T value = Ops<T>::mul(lap, Ops<T>::div(c0, D));
+    double a = __dmul_rn(__ddiv_rn(2.0, (double)D), (double)u);
+    T b = Ops<T>::mul(Ops<T>::div(N, D), prev);
+    return (T)__dadd_rn(__dsub_rn(a, (double)b), (double)value);
+}
+
+// source increment: dt^2/slowness * kws * wavelet / D           (3d/wave.c:277)
+template <typename T>
+__device__ __forceinline__ T source_term(T c0, T q, T kws, T w)
+{
+    T D = T(1);
+    if (q != T(0)) {
+        T N;
+        damping_factors(q, D, N);
+    }
+    return Ops<T>::div(Ops<T>::mul(Ops<T>::mul(c0, kws), w), D);
+}
+
+// per-point model coefficients from velocity and damping
+// slowness = 1.0/(v*v) (double divide), c0 = dt^2/slowness, q = damp*dt/(2*slowness)
+template <typename T>
+__device__ __forceinline__ void model_coefficients(T v, T damp, T dt, T dtsq, T &c0, T &q)
+{
+    T slowness = (T)__ddiv_rn(1.0, (double)Ops<T>::mul(v, v));
+    c0 = Ops<T>::div(dtsq, slowness);
+    q = Ops<T>::div(Ops<T>::mul(damp, dt), Ops<T>::mul(T(2), slowness));
+}
+
+}  // namespace sw

@@ -1,0 +1,61 @@
+"""
+Calls the CUDA backend the way simwave's Middleware does: ctypes on the
+drop-in shim library's `forward`, argtypes built from the values
+(simwave/kernel/backend/middleware.py:107-158).  Used by the GPU parity tests,
+smoke() and bench.py so that everything goes through the C ABI.
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (REPO, os.path.join(REPO, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+from simwave_b200.kernel.backend.compiler import prebuilt_library  # noqa: E402
+import oracle  # noqa: E402  (only for abi_args/_argtypes: the ABI is shared)
+
+_libs = {}
+
+
+def shim(ndim, density, dtype):
+    key = (ndim, bool(density), np.dtype(dtype).name)
+    if key not in _libs:
+        path = prebuilt_library(
+            ndim, "variable_density" if density else "constant_density",
+            "-DFLOAT" if np.dtype(dtype) == np.float32 else "-DDOUBLE")
+        lib = ctypes.CDLL(path)
+        lib.forward.restype = ctypes.c_double
+        lib.forward.argtypes = oracle._argtypes(ndim, density, dtype)
+        _libs[key] = lib
+    return _libs[key]
+
+
+def core():
+    path = os.path.join(os.path.dirname(prebuilt_library(
+        3, "constant_density", "-DFLOAT")), "libsimwave_b200.so")
+    lib = ctypes.CDLL(path)
+    lib.simwave_cuda_last_error.restype = ctypes.c_char_p
+    lib.simwave_cuda_version.restype = ctypes.c_char_p
+    lib.simwave_cuda_last_launch_count.restype = ctypes.c_ulonglong
+    lib.simwave_cuda_last_timing.argtypes = [ctypes.POINTER(ctypes.c_double)] * 4
+    return lib
+
+
+def last_timing():
+    vals = [ctypes.c_double() for _ in range(4)]
+    core().simwave_cuda_last_timing(*[ctypes.byref(v) for v in vals])
+    return dict(zip(("loop", "h2d", "d2h", "total"), [v.value for v in vals]))
+
+
+def cuda_forward(p):
+    """Run problem dict ``p`` in place through the shim's `forward`."""
+    lib = shim(p["velocity"].ndim, p.get("density") is not None,
+               p["velocity"].dtype)
+    seconds = lib.forward(*oracle.abi_args(p))
+    if seconds < 0:
+        raise RuntimeError(core().simwave_cuda_last_error().decode())
+    return seconds

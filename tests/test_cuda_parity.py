@@ -1,0 +1,252 @@
+"""
+GPU parity tests proper: the CUDA backend, called through the drop-in C ABI
+(`forward` of the shim libraries), against the CPU oracle on identical seeded
+inputs, and against the golden vectors of the unmodified reference.
+
+Tolerances (float32, from BASELINE.md / SURVEY.md section 8d):
+  * strict math mode (default): the arithmetic is rounded exactly where the
+    reference rounds it, so wavefield and receivers are required to be
+    BIT-IDENTICAL to the sequential C oracle;
+  * fast math mode: relative L2 <= 1e-5 for runs of <= 500 steps.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "oracle"))
+
+import oracle  # noqa: E402
+import problems  # noqa: E402
+import cases  # noqa: E402
+import simwave_b200 as api  # noqa: E402
+from cuda_abi import cuda_forward, core  # noqa: E402
+from conftest import rel_l2  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+REL_L2_TOL = 1e-5   # float32, <= 500 steps (north star / BASELINE.md section 3)
+
+
+def run_pair(p, env=None, monkeypatch=None):
+    a, b = problems.clone(p), problems.clone(p)
+    oracle.forward(a)
+    if env:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+    cuda_forward(b)
+    return a, b
+
+
+def assert_identical(a, b):
+    assert np.abs(a["u"]).max() > 0
+    assert np.array_equal(a["receivers"], b["receivers"]), \
+        "receivers differ: rel-L2 %.3e" % rel_l2(b["receivers"], a["receivers"])
+    assert np.array_equal(a["u"], b["u"]), \
+        "wavefield differs: rel-L2 %.3e" % rel_l2(b["u"], a["u"])
+
+
+# shape, order, density, dtype, stride, steps, bc
+ABI_CASES = [
+    ((40, 52), 2, False, np.float32, 0, 30, (2, 1, 0, 1)),
+    ((40, 52), 8, False, np.float32, 1, 30, (1, 2, 2, 0)),
+    ((44, 36), 4, True, np.float32, 2, 31, (2, 2, 2, 2)),
+    ((64, 70), 20, True, np.float64, 3, 31, (0, 1, 2, 1)),
+    ((40, 52), 6, False, np.float64, 4, 29, (1, 1, 1, 1)),
+    ((45, 50), 10, True, np.float32, 0, 40, (0, 0, 0, 0)),
+    ((20, 22, 24), 2, False, np.float32, 0, 20, (2, 1, 0, 1, 2, 1)),
+    ((30, 32, 34), 8, False, np.float32, 5, 21, (1, 2, 1, 2, 1, 2)),
+    ((24, 22, 22), 4, True, np.float32, 0, 20, (2, 2, 2, 2, 2, 2)),
+    ((22, 26, 20), 4, True, np.float32, 2, 21, (2, 1, 0, 1, 2, 1)),   # nx != ny
+    ((22, 20, 27), 6, True, np.float64, 1, 15, (0, 1, 2, 0, 1, 2)),   # nx != ny
+    ((36, 36, 36), 12, True, np.float64, 0, 12, (2, 1, 2, 1, 2, 1)),
+    ((40, 38, 42), 16, False, np.float32, 0, 16, (2, 1, 0, 1, 0, 1)),
+    ((64, 64, 64), 20, False, np.float32, 0, 10, (2, 1, 1, 1, 1, 1)),
+    ((33, 35, 37), 6, False, np.float64, 0, 18, (1, 0, 2, 2, 0, 1)),
+]
+
+
+@pytest.mark.parametrize("shape,order,density,dtype,stride,steps,bc", ABI_CASES)
+def test_strict_mode_bit_identical_to_oracle(shape, order, density, dtype,
+                                             stride, steps, bc):
+    ndim = len(shape)
+    r = order // 2
+    nbl = tuple((0, 3) if a == 0 else (2, 4) for a in range(ndim))
+    p = problems.make_problem(
+        shape=shape, space_order=order, density=density, dtype=dtype,
+        timesteps=steps, saving_stride=stride, nbl=nbl, bc=bc,
+        num_sources=3, num_receivers=9, src_radius=min(4, r + 1),
+        rec_radius=2, multi_wavelet=(stride % 2 == 0), seed=order + stride)
+    a, b = run_pair(p)
+    assert_identical(a, b)
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_sources_in_the_halo_and_on_boundary_planes(ndim):
+    """Windows that reach into the halo and sit on Dirichlet / Neumann
+    planes: the fused boundary logic must treat the increment exactly as the
+    reference's add-then-boundary sequence does."""
+    shape = (40, 44) if ndim == 2 else (30, 34, 32)
+    r = 4
+    for bc in [(2, 1) * ndim, (1, 2) * ndim, (0, 0) * ndim, (2, 2) * ndim]:
+        hi = [n - 1 for n in shape]
+        src = [[r + 0.3] * ndim, [h - r - 0.6 for h in hi],
+               [r + 1.5] + [shape[i] / 2 for i in range(1, ndim)],
+               [shape[0] / 2] * (ndim - 1) + [hi[-1] - r - 1.2]]
+        p = problems.make_problem(
+            shape=shape, space_order=8, timesteps=25, bc=bc, seed=5,
+            src_positions=np.array(src), src_radius=4, num_receivers=10,
+            rec_positions=np.array(src + [[r + 0.1] * ndim]), rec_radius=4,
+            multi_wavelet=True)
+        a, b = run_pair(p)
+        assert_identical(a, b)
+
+
+def test_overlapping_sources_keep_sequential_order():
+    """reference tests/test_parallel_solution.py geometry: nine sources whose
+    radius-8 windows overlap; sequential C adds them in index order."""
+    src = np.array([[12.0, 40.0, 13.0 + 6.4 * i] for i in range(9)])
+    p = problems.make_problem(shape=(48, 80, 84), space_order=4, timesteps=20,
+                              src_positions=src, src_radius=8,
+                              num_receivers=20, rec_radius=8, seed=2)
+    a, b = run_pair(p)
+    assert_identical(a, b)
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_fused_and_separate_boundaries_agree(ndim, monkeypatch):
+    shape = (50, 46) if ndim == 2 else (30, 28, 32)
+    p = problems.make_problem(shape=shape, space_order=6, timesteps=20,
+                              bc=(2, 1, 1, 2, 2, 2)[:2 * ndim], seed=9,
+                              num_sources=3, src_radius=3)
+    fused = problems.clone(p)
+    cuda_forward(fused)
+    monkeypatch.setenv("SIMWAVE_CUDA_BC", "separate")
+    separate = problems.clone(p)
+    cuda_forward(separate)
+    assert np.array_equal(fused["u"], separate["u"])
+    assert np.array_equal(fused["receivers"], separate["receivers"])
+
+
+def test_tiny_grid_takes_separate_boundary_path():
+    """extent < 3r+2: mirror sources are no longer interior cells."""
+    p = problems.make_problem(shape=(13, 14), space_order=8, timesteps=12,
+                              bc=(2, 2, 2, 1), num_sources=1, src_radius=1,
+                              num_receivers=3, rec_radius=1, seed=4)
+    a, b = run_pair(p)
+    assert_identical(a, b)
+
+
+@pytest.mark.parametrize("shape,order,density", [
+    ((60, 64), 8, False), ((40, 44, 48), 8, False), ((36, 36, 36), 4, True)])
+def test_fast_math_within_tolerance(shape, order, density, monkeypatch):
+    p = problems.make_problem(shape=shape, space_order=order, density=density,
+                              timesteps=60, seed=3, smooth_density=True)
+    a, b = run_pair(p, {"SIMWAVE_CUDA_MATH": "fast"}, monkeypatch)
+    assert rel_l2(b["u"], a["u"]) <= REL_L2_TOL
+    assert rel_l2(b["receivers"], a["receivers"]) <= REL_L2_TOL
+
+
+def test_nonzero_initial_fields_are_honoured():
+    """`u` is in/out: slots 0..2 may carry an initial condition."""
+    p = problems.make_problem(shape=(36, 40), space_order=4, timesteps=15,
+                              seed=8)
+    rng = np.random.default_rng(1)
+    p["u"][0] = rng.standard_normal(p["u"][0].shape).astype(np.float32) * 1e-3
+    p["u"][1] = p["u"][0] * 0.5
+    p["u"][2, :2, :] = 0.25      # halo cells of the third slot
+    a, b = run_pair(p)
+    assert_identical(a, b)
+
+
+def test_timestep_window_and_error_reporting():
+    p = problems.make_problem(shape=(30, 30), space_order=4, timesteps=12)
+    a, b = problems.clone(p), problems.clone(p)
+    for q in (a, b):
+        q["begin_timestep"], q["end_timestep"] = 3, 9
+    oracle.forward(a)
+    cuda_forward(b)
+    assert_identical(a, b)
+    bad = problems.clone(p)
+    bad["bc"][0] = 7
+    with pytest.raises(RuntimeError, match="boundary condition"):
+        cuda_forward(bad)
+    assert core().simwave_cuda_last_launch_count() > 0
+
+
+# ---------------------------------------------------------------------------
+# through the public API, against the golden vectors of the reference
+# ---------------------------------------------------------------------------
+CUDA = dict(language="cuda")
+
+
+@pytest.mark.parametrize("name", sorted(cases.SMALL_CASES))
+def test_small_cases_match_reference_golden(golden, name):
+    ref = golden("forward_small")
+    solver = cases.small_solver(api, name, api.Compiler(**CUDA))
+    u, recv = solver.forward()
+    assert np.array_equal(recv, ref[name + "/recv"])
+    assert np.array_equal(u[ref[name + "/u_idx"]], ref[name + "/u"])
+
+
+@pytest.mark.parametrize("dimension,space_order,density", [
+    (2, 2, False), (2, 8, False), (3, 2, False), (3, 8, False),
+    (2, 2, True), (3, 2, True)])
+def test_solution(golden, dimension, space_order, density):
+    """Reference tests/test_solution.py with language='cuda': the reference's
+    own .npy within its GPU bar atol=1e-4 (tests/test_gpu_solution.py:139)
+    and its CPU bar atol=1e-5; the regenerated field bit for bit."""
+    ref = golden("solution_%dd_so%d" % (dimension, space_order))
+    solver = cases.solution_solver(api, dimension, space_order,
+                                   api.Compiler(**CUDA), density=density)
+    u, recv = solver.forward()
+    if dimension == 2:
+        assert np.allclose(u, ref["u_reference_npy"], atol=1e-5)
+        if not density:
+            assert np.array_equal(u, ref["u"])
+            assert np.array_equal(recv, ref["recv"])
+        else:
+            assert np.allclose(u, ref["u"], atol=1e-5)
+    else:
+        f = u[0]
+        c = [n // 2 for n in f.shape]
+        planes = (f[c[0]], f[:, c[1]], f[:, :, c[2]])
+        for got, key in zip(planes, ("plane_z", "plane_x", "plane_y")):
+            if density:
+                assert np.allclose(got, ref[key], atol=1e-5)
+            else:
+                assert np.array_equal(got, ref[key])
+
+
+@pytest.mark.parametrize("dimension,density", [(2, False), (3, False),
+                                               (2, True), (3, True)])
+def test_parallel_solution_f64(golden, dimension, density):
+    """Reference tests/test_parallel_solution.py (float64, atol=1e-8)."""
+    ref = golden("parallel_f64")
+    tag = "{}d_{}".format(dimension, "var" if density else "const")
+    solver = cases.parallel_solver(api, dimension, density, np.float64,
+                                   api.Compiler(**CUDA))
+    u, recv = solver.forward()
+    assert np.allclose(recv, ref[tag + "/recv"], atol=1e-8)
+    if dimension == 2:
+        assert np.allclose(u, ref[tag + "/u"], atol=1e-8)
+    else:
+        f = u[0]
+        c = [n // 2 for n in f.shape]
+        assert np.allclose(f[c[0]], ref[tag + "/plane_z"], atol=1e-8)
+        assert np.allclose(f[:, :, c[2]], ref[tag + "/plane_y"], atol=1e-8)
+
+
+@pytest.mark.parametrize("dimension,density,stride", [
+    (2, False, 1), (2, False, 2), (2, False, 5), (2, True, 2),
+    (3, False, 1), (3, False, 2), (3, False, 3), (3, False, 4), (3, True, 5)])
+def test_u_saving(dimension, density, stride):
+    """Reference tests/test_u_saving.py: the last saved snapshot is
+    bit-identical whatever the saving stride."""
+    comp = api.Compiler(**CUDA)
+    base, _ = cases.u_saving_solver(api, dimension, density, 0, comp).forward()
+    last, _ = cases.u_saving_solver(api, dimension, density, stride,
+                                    comp).forward()
+    assert np.array_equal(base[-1], last[-1])

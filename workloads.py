@@ -1,0 +1,222 @@
+"""
+Synthetic versions of the five BASELINE.json configurations, built as the
+arrays the `forward` C-ABI receives.  The big 3D models
+are built directly in their extended (halo + damping layer) form: pushing a
+10^8..10^9-point model through SpaceModel.interpolate needs tens of GB of
+float64 temporaries, and the kernel only ever sees the
+extended arrays anyway.  Geometry, boundary conditions, source / receiver
+layout and wavelets follow the reference's benchmark scripts.
+"""
+import numpy as np
+
+from simwave_b200.kernel.frontend import fd, kws
+
+BC = {"none": 0, "null_dirichlet": 1, "null_neumann": 2}
+
+
+def _tables(shape, positions, radius, dtype):
+    intervals, values, offsets = [], [], [0]
+    for pos in positions:
+        p, v = kws.get_source_points(shape, [dtype(x) for x in pos], radius)
+        intervals.append(p)
+        values.append(v)
+        offsets.append(offsets[-1] + v.size)
+    return (np.concatenate(intervals).astype(np.uint64),
+            np.concatenate(values).astype(dtype),
+            np.asarray(offsets, dtype=np.uint64))
+
+
+def _damping(inner_shape, nbl, halo, alpha, degree, dtype):
+    mask = np.pad(np.zeros(inner_shape, dtype=dtype), nbl, mode="linear_ramp",
+                  end_values=nbl)
+    mask = (mask ** degree) * alpha
+    return np.pad(mask, [(halo, halo)] * len(inner_shape)).astype(dtype)
+
+
+def _extend(model, nbl, halo):
+    pad = [(b + halo, a + halo) for b, a in nbl]
+    return np.ascontiguousarray(np.pad(model, pad, mode="edge"))
+
+
+def _ricker(f0, t0, tf, timesteps, dtype):
+    t = np.linspace(dtype(t0), dtype(tf), timesteps, dtype=dtype)
+    arg = np.pi * f0 * (t - 1 / f0)
+    return (1 * (1 - 2.0 * arg ** 2) * np.exp(-arg ** 2)).astype(dtype)
+
+
+def _assemble(velocity, density, nbl, spacing, space_order, bc, src_coords,
+              rec_coords, radius, f0, tf, timesteps, alpha=0.001, degree=3,
+              dtype=np.float32, saving_stride=0, name=""):
+    """velocity/density: physical-domain models; coords in metres."""
+    dtype = np.dtype(dtype).type
+    ndim = velocity.ndim
+    r = space_order // 2
+    inner = tuple(n + b + a for n, (b, a) in zip(velocity.shape, nbl))
+    ext_v = _extend(velocity.astype(dtype), nbl, r)
+    ext_d = None if density is None else _extend(density.astype(dtype), nbl, r)
+    damp = _damping(velocity.shape, nbl, r, alpha, degree, dtype)
+    shape = ext_v.shape
+    h = [dtype(x) for x in spacing]
+    dt = dtype(fd.calculate_dt(ndim, space_order, h, velocity.astype(dtype)))
+    full_steps = int(np.ceil((dtype(tf) - dtype(0) + dt) / dt))
+    if timesteps is None:
+        timesteps = full_steps
+
+    def to_grid(coords):
+        origin = np.array([b + r for b, _ in nbl], dtype=dtype)
+        return np.asarray(coords, dtype=dtype) / np.array(h, dtype=dtype) + origin
+
+    src_iv, src_val, src_off = _tables(shape, to_grid(src_coords), radius, dtype)
+    rec_iv, rec_val, rec_off = _tables(shape, to_grid(rec_coords), radius, dtype)
+    wavelet = _ricker(f0, 0.0, tf, full_steps, dtype)[:timesteps].copy()
+    slots = 3 if saving_stride == 0 else \
+        len(range(0, timesteps, saving_stride)) + 2
+    del inner
+    return {
+        "name": name,
+        "u": np.zeros((slots,) + shape, dtype=dtype),
+        "velocity": ext_v, "density": ext_d, "damp": damp,
+        "wavelet": wavelet,
+        "coeff2": dtype(fd.half_coefficients(2, space_order)),
+        "coeff1": dtype(fd.half_coefficients(1, space_order)),
+        "bc": np.asarray([BC[b] for b in bc], dtype=np.uint64),
+        "src_intervals": src_iv, "src_values": src_val, "src_offsets": src_off,
+        "rec_intervals": rec_iv, "rec_values": rec_val, "rec_offsets": rec_off,
+        "receivers": np.zeros((timesteps, len(rec_off) - 1), dtype=dtype),
+        "spacing": spacing, "saving_stride": saving_stride, "dt": dt,
+        "end_timestep": timesteps, "space_order": space_order,
+        "full_timesteps": full_steps,
+    }
+
+
+def interior_points(p):
+    r = p["space_order"] // 2
+    return int(np.prod([n - 2 * r for n in p["velocity"].shape]))
+
+
+def bytes_per_point(p):
+    """Algorithmic bytes per grid-point update:
+    read u_prev, u_cur, velocity, damp (+density), write u_next."""
+    fields = 5 + (1 if p.get("density") is not None else 0)
+    return fields * p["velocity"].dtype.itemsize
+
+
+# ---------------------------------------------------------------------------
+def readme_2d(timesteps=None):
+    """C1: README 2D two-layer model (reference README.md:54-137)."""
+    vel = np.full((513, 513), 1500.0, dtype=np.float32)
+    vel[257:] = 2000.0
+    return _assemble(
+        vel, None, ((0, 0), (0, 0)), (10.0, 10.0), 4,
+        ("null_neumann", "null_dirichlet", "none", "null_dirichlet"),
+        [(2560.0, 2560.0)], [(2560.0, 10.0 * i) for i in range(512)],
+        1, 10.0, 1.0, timesteps, name="readme_2d")
+
+
+def marmousi_2d(space_order=8, timesteps=None, seed=1):
+    """C2: Marmousi-shaped 351 x 1701 model (benchmark/marmousi_2D.py:71-113)."""
+    nz, nx = 351, 1701
+    rng = np.random.default_rng(seed)
+    z = np.arange(nz, dtype=np.float64)[:, None]
+    x = np.arange(nx, dtype=np.float64)[None, :]
+    vel = 1500.0 + (4700.0 - 1500.0) * (z / (nz - 1)) + 0.0 * x
+    for k in range(8):                       # dipping reflector steps
+        depth = 60 + 35 * k + 0.02 * (k + 1) * x
+        vel = vel + 120.0 * (z > depth)
+    coarse = rng.standard_normal((12, 40))
+    smooth = np.kron(coarse, np.ones((30, 43)))[:nz, :nx]
+    vel = vel * (1.0 + 0.03 * np.tanh(smooth))
+    vel[:20] = 1500.0                        # water layer
+    vel = np.clip(vel, 1028.0, 4700.0).astype(np.float32)
+    return _assemble(
+        vel, None, ((0, 70), (70, 70)), (10.0, 10.0), space_order,
+        ("null_neumann", "null_dirichlet", "null_dirichlet", "null_dirichlet"),
+        [(20.0, 8500.0)], [(20.0, 10.0 * i) for i in range(1700)],
+        1, 10.0, 2.0, timesteps, name="marmousi_2d")
+
+
+def _layered_3d(shape, vmin, vmax, seed, step_axis=2):
+    nz = shape[0]
+    rng = np.random.default_rng(seed)
+    z = np.arange(nz, dtype=np.float32)[:, None, None]
+    vel = np.empty(shape, dtype=np.float32)
+    vel[:] = vmin + (vmax - vmin) * (z / (nz - 1))
+    # thrust-like lateral step: layers shifted upwards on one side
+    half = shape[step_axis] // 2
+    shift = max(1, nz // 10)
+    idx = [slice(None)] * 3
+    idx[step_axis] = slice(half, None)
+    shifted = np.roll(vel[tuple(idx)], -shift, axis=0)
+    shifted[-shift:] = vmax
+    vel[tuple(idx)] = shifted
+    coarse = rng.standard_normal(tuple((n + 31) // 32 for n in shape)).astype(np.float32)
+    pert = np.kron(coarse, np.ones((32, 32, 32), dtype=np.float32))
+    pert = pert[:shape[0], :shape[1], :shape[2]]
+    vel *= (1.0 + 0.03 * np.tanh(pert))
+    return np.clip(vel, vmin, vmax).astype(np.float32)
+
+
+def overthrust_3d(space_order=8, timesteps=None, seed=2):
+    """C3: Overthrust-shaped 207 x 801 x 801 model, no damping layer
+    (benchmark/overthrust_3D.py:77-114)."""
+    vel = _layered_3d((207, 801, 801), 2179.0, 6000.0, seed)
+    return _assemble(
+        vel, None, ((0, 0),) * 3, (20.0, 20.0, 20.0), space_order,
+        ("null_neumann", "null_dirichlet", "null_dirichlet", "null_dirichlet",
+         "null_dirichlet", "null_dirichlet"),
+        [(20.0, 8000.0, 8000.0)],
+        [(20.0, 8000.0, 20.0 * i) for i in range(800)],
+        1, 8.0, 4.0, timesteps, name="overthrust_3d")
+
+
+def variable_density_3d(n=1024, space_order=16, timesteps=200, nz=None):
+    """C4: n^3 variable density, order 16, 40-point cubic damping layers on
+    every side but the top.  Built directly in extended form.  ``nz`` selects
+    a slab height (weak-scaling runs stack slabs along z)."""
+    r = space_order // 2
+    nbl = ((0, 40), (40, 40), (40, 40))
+    nz = n if nz is None else nz
+    phys = tuple(m - b - a for m, (b, a) in zip((nz, n, n), nbl))
+    rng3, rng4 = np.random.default_rng(3), np.random.default_rng(4)
+
+    def smooth(rng):
+        coarse = rng.random(tuple((m + 63) // 64 + 1 for m in phys)).astype(np.float32)
+        up = np.kron(coarse, np.ones((64, 64, 64), dtype=np.float32))
+        return up[:phys[0], :phys[1], :phys[2]]
+
+    vel = (1500.0 + 3000.0 * smooth(rng3)).astype(np.float32)
+    den = (1000.0 + 1500.0 * smooth(rng4)).astype(np.float32)
+    h = (10.0, 10.0, 10.0)
+    size = [(m - 1) * s for m, s in zip(phys, h)]
+    src = [(20.0, size[1] / 2, size[2] / 2)]
+    rec = [(20.0, size[1] / 2, size[2] * i / 1023.0) for i in range(1024)]
+    p = _assemble(
+        vel, den, nbl, h, space_order,
+        ("null_neumann", "null_dirichlet", "null_dirichlet", "null_dirichlet",
+         "null_dirichlet", "null_dirichlet"),
+        src, rec, 4, 8.0, 4.0, timesteps, name="variable_density_3d")
+    del r
+    return p
+
+
+def shot_3d(shot=0, n=512, space_order=8, timesteps=300, seed=5):
+    """C5: one shot of the 64-shot survey over a shared n^3 model."""
+    vel = _layered_3d((n, n, n), 1500.0, 4500.0, seed)
+    h = (10.0, 10.0, 10.0)
+    x = 80.0 * shot + 40.0
+    rec = [(20.0, x, 10.0 * i) for i in range(n)]
+    return _assemble(
+        vel, None, ((0, 0),) * 3, h, space_order,
+        ("null_neumann", "null_dirichlet", "null_dirichlet", "null_dirichlet",
+         "null_dirichlet", "null_dirichlet"),
+        [(20.0, x, (n - 1) * 5.0)], rec, 4, 10.0, 2.0, timesteps,
+        name="shot_3d")
+
+
+WORKLOADS = {
+    "readme_2d": readme_2d,
+    "marmousi_2d": marmousi_2d,
+    "overthrust_3d": overthrust_3d,
+    "variable_density_3d": variable_density_3d,
+    "shot_3d": shot_3d,
+}

@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <type_traits>
+
 #include "sw_launch.h"
 #include "sw_points.cuh"
 
@@ -211,6 +213,40 @@ static dim3 row_grid(const Grid &g)
 }
 
 // ---------------------------------------------------------------------------
+// tiled 3D kernel plumbing
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        SW_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p)
+            throw Error("driver does not provide cuTensorMapEncodeTiled");
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+typedef bool (*TiledQueryFn)(int, TiledInfo *);
+typedef bool (*TiledLaunchFn)(int, int, const StepArgs<float> &, const CUtensorMap &, int,
+                              cudaStream_t);
+static const TiledQueryFn kTiledQuery[kMaxRadius + 1] = {
+    nullptr, tiled3d_query_r1, tiled3d_query_r2, tiled3d_query_r3, tiled3d_query_r4,
+    tiled3d_query_r5, tiled3d_query_r6, tiled3d_query_r7, tiled3d_query_r8, tiled3d_query_r9,
+    tiled3d_query_r10};
+static const TiledLaunchFn kTiledLaunch[kMaxRadius + 1] = {
+    nullptr, tiled3d_launch_r1, tiled3d_launch_r2, tiled3d_launch_r3, tiled3d_launch_r4,
+    tiled3d_launch_r5, tiled3d_launch_r6, tiled3d_launch_r7, tiled3d_launch_r8,
+    tiled3d_launch_r9, tiled3d_launch_r10};
+
+// ---------------------------------------------------------------------------
 // Plan
 // ---------------------------------------------------------------------------
 template <typename T>
@@ -260,6 +296,15 @@ private:
     int srcMode_ = SRC_DISJOINT;
     int srcMaxPoints_ = 1;
     StepFn stepSimple_ = nullptr;
+
+    // tiled 3D kernel (float32, constant density)
+    bool useTiled_ = false;
+    int tiledCfg_ = 0;
+    int zChunk_ = 0;
+    TiledInfo tiledInfo_{};
+    std::map<const void *, CUtensorMap> maps_;
+    const CUtensorMap &field_map(const T *base);
+    void choose_tiling();
 
     cudaStream_t stream_ = nullptr;
     cudaEvent_t evBegin_ = nullptr, evEnd_ = nullptr;
@@ -471,6 +516,8 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     else
         stepSimple_ = varden_ ? &launch_step_simple<T, 2, true> : &launch_step_simple<T, 2, false>;
 
+    choose_tiling();
+
     // ---- which of the caller's slots start as zeros ----------------------------
     slotZero_.assign(numSlots_, 0);
     if (all_zero(hostU_, numSlots_ * denseCells_ * sizeof(T))) {
@@ -597,8 +644,84 @@ void Plan<T>::retire_below(size_t bound)
 }
 
 template <typename T>
+void Plan<T>::choose_tiling()
+{
+    useTiled_ = false;
+    if constexpr (std::is_same<T, float>::value) {
+        if (opt_.simple || ndim_ != 3 || varden_)
+            return;
+        const int r = g_.r;
+        // default configuration, overridable as SIMWAVE_CUDA_TILE=<cfg>[:<zchunk>]
+        int cfg = (r <= 5) ? 2 : 0;
+        int zchunk = 0;
+        if (const char *e = std::getenv("SIMWAVE_CUDA_TILE")) {
+            cfg = std::atoi(e);
+            if (const char *c = std::strchr(e, ':'))
+                zchunk = std::atoi(c + 1);
+        }
+        if (!kTiledQuery[r](cfg, &tiledInfo_))
+            throw Error("SIMWAVE_CUDA_TILE: no such tile configuration");
+        int maxSmem = 0;
+        SW_CUDA(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
+        if (tiledInfo_.smemBytes > maxSmem)
+            return;   // plain kernel
+        tiledCfg_ = cfg;
+        const int interior = g_.nS - 2 * r;
+        if (zchunk <= 0) {
+            // enough CTAs for a few waves, but chunks long enough that the
+            // 2r priming planes stay a small fraction of the traffic
+            int sms = 148;
+            SW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_));
+            const long long tiles =
+                (long long)((g_.nF - 2 * r + tiledInfo_.tileF() - 1) / tiledInfo_.tileF()) *
+                ((g_.nM - 2 * r + tiledInfo_.tileM() - 1) / tiledInfo_.tileM());
+            const long long want = 6LL * sms;
+            int chunks = (int)std::max<long long>(1, (want + tiles - 1) / tiles);
+            chunks = std::min(chunks, std::max(1, interior / (6 * r)));
+            zchunk = (interior + chunks - 1) / chunks;
+        }
+        zChunk_ = std::max(1, std::min(zchunk, interior));
+        useTiled_ = true;
+    }
+}
+
+template <typename T>
+const CUtensorMap &Plan<T>::field_map(const T *base)
+{
+    auto it = maps_.find(base);
+    if (it != maps_.end())
+        return it->second;
+    CUtensorMap m;
+    // the tensor starts at the beginning of the padded row, so that its base
+    // is 16-byte aligned for any radius; coordinates are shifted by lpad
+    void *rowStart = (void *)(base - g_.lpad);
+    const cuuint64_t dims[3] = {(cuuint64_t)g_.pitch, (cuuint64_t)g_.nM, (cuuint64_t)g_.nS};
+    const cuuint64_t strides[2] = {(cuuint64_t)g_.pitch * sizeof(T),
+                                   (cuuint64_t)g_.planeStride * sizeof(T)};
+    const int rp = (g_.r + 3) / 4 * 4;
+    const cuuint32_t box[3] = {(cuuint32_t)(tiledInfo_.tileF() + 2 * rp),
+                               (cuuint32_t)(tiledInfo_.tileM() + 2 * g_.r), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult rc = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, rowStart, dims, strides,
+                                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS)
+        throw Error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)rc));
+    return maps_.emplace(base, m).first->second;
+}
+
+template <typename T>
 void Plan<T>::launch_step(const StepArgs<T> &a)
 {
+    if constexpr (std::is_same<T, float>::value) {
+        if (useTiled_) {
+            if (!kTiledLaunch[g_.r](tiledCfg_, opt_.math, a, field_map(a.cur), zChunk_, stream_))
+                throw Error("tiled kernel configuration vanished");
+            check_launch("tiled step kernel");
+            return;
+        }
+    }
     stepSimple_(opt_.math, a, stream_);
     check_launch("step kernel");
 }

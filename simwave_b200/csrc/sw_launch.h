@@ -11,4 +11,24 @@ namespace sw {
 template <typename T, int NDIM, bool VARDEN>
 void launch_step_simple(int math, const StepArgs<T> &a, cudaStream_t stream);
 
+// ---- tiled 3D kernel (float32, constant density) ---------------------------
+struct TiledInfo {
+    int pm, tx, ty, pf;     // points per thread along M, thread columns / rows, prefetch depth
+    int smemBytes;
+    int tileM() const { return ty * pm; }
+    int tileF() const { return tx * 4; }
+};
+
+}  // namespace sw
+
+#include <cuda.h>
+
+namespace sw {
+#define SW_DECL_TILED(R)                                                              \
+    bool tiled3d_query_r##R(int cfg, TiledInfo *info);                                \
+    bool tiled3d_launch_r##R(int cfg, int math, const StepArgs<float> &a,             \
+                             const CUtensorMap &map, int zChunk, cudaStream_t stream);
+SW_DECL_TILED(1) SW_DECL_TILED(2) SW_DECL_TILED(3) SW_DECL_TILED(4) SW_DECL_TILED(5)
+SW_DECL_TILED(6) SW_DECL_TILED(7) SW_DECL_TILED(8) SW_DECL_TILED(9) SW_DECL_TILED(10)
+#undef SW_DECL_TILED
 }  // namespace sw

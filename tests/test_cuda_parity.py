@@ -250,3 +250,56 @@ def test_u_saving(dimension, density, stride):
     last, _ = cases.u_saving_solver(api, dimension, density, stride,
                                     comp).forward()
     assert np.array_equal(base[-1], last[-1])
+
+
+# ---------------------------------------------------------------------------
+# tiled 3D kernel: every radius and tile configuration against the plain kernel
+# ---------------------------------------------------------------------------
+def _tiled_vs_plain(order, tile, monkeypatch, shape=(37, 75, 150), steps=6,
+                    bc=(2, 1, 2, 1, 2, 1), math="strict"):
+    r = order // 2
+    p = problems.make_problem(
+        shape=shape, space_order=order, timesteps=steps, bc=bc, seed=order,
+        nbl=((0, 3), (2, 2), (3, 2)), num_sources=2, src_radius=min(4, r + 1),
+        num_receivers=6, rec_radius=2)
+    monkeypatch.setenv("SIMWAVE_CUDA_MATH", math)
+    monkeypatch.setenv("SIMWAVE_CUDA_KERNEL", "simple")
+    plain = problems.clone(p)
+    cuda_forward(plain)
+    monkeypatch.setenv("SIMWAVE_CUDA_KERNEL", "auto")
+    monkeypatch.setenv("SIMWAVE_CUDA_TILE", tile)
+    tiled = problems.clone(p)
+    cuda_forward(tiled)
+    assert np.abs(plain["u"]).max() > 0
+    return plain, tiled
+
+
+@pytest.mark.parametrize("order", [2, 4, 6, 8, 10, 12, 14, 16, 18, 20])
+def test_tiled_kernel_every_radius(order, monkeypatch):
+    for cfg in (0, 1, 2):
+        plain, tiled = _tiled_vs_plain(order, "%d:11" % cfg, monkeypatch)
+        assert np.array_equal(plain["u"], tiled["u"]), (order, cfg)
+        assert np.array_equal(plain["receivers"], tiled["receivers"])
+
+
+@pytest.mark.parametrize("cfg", range(7))
+@pytest.mark.parametrize("bc", [(2, 2, 2, 2, 2, 2), (1, 1, 1, 1, 1, 1),
+                                (0, 2, 1, 0, 2, 1)])
+def test_tiled_kernel_every_configuration(cfg, bc, monkeypatch):
+    for zchunk in (0, 5, 1000):
+        plain, tiled = _tiled_vs_plain(8, "%d:%d" % (cfg, zchunk), monkeypatch,
+                                       shape=(41, 70, 203), bc=bc)
+        assert np.array_equal(plain["u"], tiled["u"]), (cfg, zchunk)
+
+
+def test_tiled_kernel_fast_math_matches_plain_fast_math(monkeypatch):
+    plain, tiled = _tiled_vs_plain(8, "2:0", monkeypatch, math="fast")
+    assert rel_l2(tiled["u"], plain["u"]) <= 1e-6
+
+
+def test_tiled_kernel_in_place_between_snapshots(monkeypatch):
+    """saving_stride > 1: the reference updates in place (next == prev)."""
+    p = problems.make_problem(shape=(30, 50, 90), space_order=8, timesteps=21,
+                              saving_stride=4, seed=6)
+    a, b = run_pair(p)
+    assert_identical(a, b)

@@ -29,7 +29,8 @@
  *    The `forward` signature is frozen, so every new knob lives here or in
  *    environment variables:
  *        SIMWAVE_CUDA_DEVICE   device ordinal used by `forward` (default: current)
- *        SIMWAVE_CUDA_MATH     strict | fast  (default strict)
+ *        SIMWAVE_CUDA_MATH     fast | strict  (default fast; strict is bit-identical
+ *                              to the reference's sequential C kernel)
  *        SIMWAVE_CUDA_KERNEL   auto | simple  (auto picks the tiled kernels)
  *        SIMWAVE_CUDA_DEBUG    1 = synchronise and check after every launch
  */

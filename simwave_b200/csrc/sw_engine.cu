@@ -40,7 +40,7 @@ static bool env_is(const char *name, const char *value)
 Options Options::from_env()
 {
     Options o;
-    o.math = env_is("SIMWAVE_CUDA_MATH", "fast") ? MATH_FAST : MATH_STRICT;
+    o.math = env_is("SIMWAVE_CUDA_MATH", "strict") ? MATH_STRICT : MATH_FAST;
     o.simple = env_is("SIMWAVE_CUDA_KERNEL", "simple");
     o.debug = env_is("SIMWAVE_CUDA_DEBUG", "1");
     o.separateBc = env_is("SIMWAVE_CUDA_BC", "separate");
@@ -235,8 +235,8 @@ static EncodeTiledFn encode_tiled_fn()
 }
 
 typedef bool (*TiledQueryFn)(int, TiledInfo *);
-typedef bool (*TiledLaunchFn)(int, int, const StepArgs<float> &, const CUtensorMap &, int,
-                              cudaStream_t);
+typedef bool (*TiledLaunchFn)(int, int, const StepArgs<float> &, const StepMaps &,
+                              const unsigned char *, int, cudaStream_t);
 static const TiledQueryFn kTiledQuery[kMaxRadius + 1] = {
     nullptr, tiled3d_query_r1, tiled3d_query_r2, tiled3d_query_r3, tiled3d_query_r4,
     tiled3d_query_r5, tiled3d_query_r6, tiled3d_query_r7, tiled3d_query_r8, tiled3d_query_r9,
@@ -302,9 +302,10 @@ private:
     int tiledCfg_ = 0;
     int zChunk_ = 0;
     TiledInfo tiledInfo_{};
-    std::map<const void *, CUtensorMap> maps_;
-    const CUtensorMap &field_map(const T *base);
+    std::map<std::pair<const void *, bool>, CUtensorMap> maps_;
+    const CUtensorMap &field_map(const T *base, bool halo);
     void choose_tiling();
+    DeviceBuffer qflags_;   // [nS][tilesM][tilesF]: damping profile non-zero in the tile?
 
     cudaStream_t stream_ = nullptr;
     cudaEvent_t evBegin_ = nullptr, evEnd_ = nullptr;
@@ -407,6 +408,16 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
         a.inv_h2[i] = T(1) / a.h2[i];
         volatile T f4 = T(4) * a.h2[i];
         a.four_h2[i] = f4;
+    }
+    // fast math: coefficients pre-divided by h^2
+    {
+        T sumInv = T(0);
+        for (int ax = (ndim_ == 3 ? 0 : 1); ax < 3; ax++) {
+            sumInv += a.inv_h2[ax];
+            for (int i = 0; i <= r; i++)
+                a.cs[ax][i] = a.c2[i] * a.inv_h2[ax];
+        }
+        a.cc = a.c2[0] * sumInv;
     }
     const size_t *bc = pb.boundary_conditions;
     if (ndim_ == 3) {
@@ -652,7 +663,7 @@ void Plan<T>::choose_tiling()
             return;
         const int r = g_.r;
         // default configuration, overridable as SIMWAVE_CUDA_TILE=<cfg>[:<zchunk>]
-        int cfg = (r <= 5) ? 2 : 0;
+        int cfg = (r <= 5) ? 6 : 0;
         int zchunk = 0;
         if (const char *e = std::getenv("SIMWAVE_CUDA_TILE")) {
             cfg = std::atoi(e);
@@ -667,28 +678,64 @@ void Plan<T>::choose_tiling()
             return;   // plain kernel
         tiledCfg_ = cfg;
         const int interior = g_.nS - 2 * r;
+        const long long tilesF = (g_.nF - 2 * r + tiledInfo_.tileF() - 1) / tiledInfo_.tileF();
+        const long long tilesM = (g_.nM - 2 * r + tiledInfo_.tileM() - 1) / tiledInfo_.tileM();
         if (zchunk <= 0) {
-            // enough CTAs for a few waves, but chunks long enough that the
-            // 2r priming planes stay a small fraction of the traffic
+            // Split S into chunks so that the CTAs fill whole waves (a wave =
+            // SMs x resident CTAs), against the cost of a chunk's 2r priming
+            // planes of u_cur (re-read by the neighbouring chunk).
             int sms = 148;
             SW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_));
-            const long long tiles =
-                (long long)((g_.nF - 2 * r + tiledInfo_.tileF() - 1) / tiledInfo_.tileF()) *
-                ((g_.nM - 2 * r + tiledInfo_.tileM() - 1) / tiledInfo_.tileM());
-            const long long want = 6LL * sms;
-            int chunks = (int)std::max<long long>(1, (want + tiles - 1) / tiles);
-            chunks = std::min(chunks, std::max(1, interior / (6 * r)));
-            zchunk = (interior + chunks - 1) / chunks;
+            int maxSmemSm = 0;
+            SW_CUDA(cudaDeviceGetAttribute(&maxSmemSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor,
+                                           device_));
+            const int threads = tiledInfo_.tx * tiledInfo_.ty + 32;
+            int resident = std::max(1, std::min(maxSmemSm / (tiledInfo_.smemBytes + 1024),
+                                                2048 / threads));
+            resident = std::min(resident, tiledInfo_.minBlocks);
+            const double slots = (double)sms * resident;
+            const double haloBytes = 4.0 * (tiledInfo_.tileM() + 2 * r) *
+                                     (tiledInfo_.tileF() + 2 * ((r + 3) / 4 * 4)) /
+                                     ((double)tiledInfo_.tileM() * tiledInfo_.tileF());
+            double best = -1;
+            int bestChunks = 1;
+            for (int chunks = 1; chunks <= 64 && interior / chunks >= 2 * r; chunks++) {
+                const int len = (interior + chunks - 1) / chunks;
+                const int real = (interior + len - 1) / len;
+                const double waves = tilesF * tilesM * real / slots;
+                const double fill = waves / std::ceil(waves);
+                const double traffic = 20.0 / (20.0 + 2.0 * r * haloBytes / len);
+                const double score = fill * traffic;
+                if (score > best + 1e-9) { best = score; bestChunks = chunks; }
+            }
+            zchunk = (interior + bestChunks - 1) / bestChunks;
         }
         zChunk_ = std::max(1, std::min(zchunk, interior));
         useTiled_ = true;
+
+        // per (plane, tile) flag: does the damping profile act inside the tile?
+        qflags_.alloc((size_t)g_.nS * tilesM * tilesF);
+        SW_CUDA(cudaMemsetAsync(qflags_.get(), 0, qflags_.bytes(), stream_));
+        dim3 grid((unsigned)tilesF, (unsigned)tilesM, (unsigned)interior);
+        qflag_kernel<<<grid, 128, 0, stream_>>>(g_, field_base(q_), tiledInfo_.tileM(),
+                                                tiledInfo_.tileF(),
+                                                qflags_.as<unsigned char>());
+        check_launch("qflag_kernel");
+        if (std::getenv("SIMWAVE_CUDA_VERBOSE"))
+            std::fprintf(stderr,
+                         "simwave_b200: tiled 3D kernel cfg %d, tile %dx%d, z chunk %d (%d chunks), "
+                         "grid %lldx%lldx%d, smem %d B\n",
+                         tiledCfg_, tiledInfo_.tileM(), tiledInfo_.tileF(), zChunk_,
+                         (interior + zChunk_ - 1) / zChunk_, tilesF, tilesM,
+                         (interior + zChunk_ - 1) / zChunk_, tiledInfo_.smemBytes);
     }
 }
 
 template <typename T>
-const CUtensorMap &Plan<T>::field_map(const T *base)
+const CUtensorMap &Plan<T>::field_map(const T *base, bool halo)
 {
-    auto it = maps_.find(base);
+    const auto key = std::make_pair((const void *)base, halo);
+    auto it = maps_.find(key);
     if (it != maps_.end())
         return it->second;
     CUtensorMap m;
@@ -699,8 +746,8 @@ const CUtensorMap &Plan<T>::field_map(const T *base)
     const cuuint64_t strides[2] = {(cuuint64_t)g_.pitch * sizeof(T),
                                    (cuuint64_t)g_.planeStride * sizeof(T)};
     const int rp = (g_.r + 3) / 4 * 4;
-    const cuuint32_t box[3] = {(cuuint32_t)(tiledInfo_.tileF() + 2 * rp),
-                               (cuuint32_t)(tiledInfo_.tileM() + 2 * g_.r), 1};
+    const cuuint32_t box[3] = {(cuuint32_t)(tiledInfo_.tileF() + (halo ? 2 * rp : 0)),
+                               (cuuint32_t)(tiledInfo_.tileM() + (halo ? 2 * g_.r : 0)), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult rc = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, rowStart, dims, strides,
                                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -708,7 +755,7 @@ const CUtensorMap &Plan<T>::field_map(const T *base)
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS)
         throw Error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)rc));
-    return maps_.emplace(base, m).first->second;
+    return maps_.emplace(key, m).first->second;
 }
 
 template <typename T>
@@ -716,7 +763,13 @@ void Plan<T>::launch_step(const StepArgs<T> &a)
 {
     if constexpr (std::is_same<T, float>::value) {
         if (useTiled_) {
-            if (!kTiledLaunch[g_.r](tiledCfg_, opt_.math, a, field_map(a.cur), zChunk_, stream_))
+            StepMaps maps;
+            maps.cur = field_map(a.cur, true);
+            maps.prev = field_map(a.prev, false);
+            maps.c0 = field_map(a.c0, false);
+            maps.q = field_map(a.q, false);
+            if (!kTiledLaunch[g_.r](tiledCfg_, opt_.math, a, maps, qflags_.as<unsigned char>(),
+                                    zChunk_, stream_))
                 throw Error("tiled kernel configuration vanished");
             check_launch("tiled step kernel");
             return;

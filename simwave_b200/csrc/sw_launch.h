@@ -13,7 +13,8 @@ void launch_step_simple(int math, const StepArgs<T> &a, cudaStream_t stream);
 
 // ---- tiled 3D kernel (float32, constant density) ---------------------------
 struct TiledInfo {
-    int pm, tx, ty, pf;     // points per thread along M, thread columns / rows, prefetch depth
+    int pm, tx, ty, pf, ps; // points per thread along M, thread columns / rows, prefetch depths
+    int minBlocks;          // CTAs per SM the kernel was compiled for
     int smemBytes;
     int tileM() const { return ty * pm; }
     int tileF() const { return tx * 4; }
@@ -24,10 +25,15 @@ struct TiledInfo {
 #include <cuda.h>
 
 namespace sw {
+// tensor maps of one time step: u_cur with halo; u_prev, c0, q halo-free
+struct StepMaps {
+    CUtensorMap cur, prev, c0, q;
+};
 #define SW_DECL_TILED(R)                                                              \
     bool tiled3d_query_r##R(int cfg, TiledInfo *info);                                \
     bool tiled3d_launch_r##R(int cfg, int math, const StepArgs<float> &a,             \
-                             const CUtensorMap &map, int zChunk, cudaStream_t stream);
+                             const StepMaps &maps, const unsigned char *qflags,       \
+                             int zChunk, cudaStream_t stream);
 SW_DECL_TILED(1) SW_DECL_TILED(2) SW_DECL_TILED(3) SW_DECL_TILED(4) SW_DECL_TILED(5)
 SW_DECL_TILED(6) SW_DECL_TILED(7) SW_DECL_TILED(8) SW_DECL_TILED(9) SW_DECL_TILED(10)
 #undef SW_DECL_TILED

@@ -36,6 +36,25 @@ __global__ void model_kernel(Grid g, const T *__restrict__ velocity, const T *__
         }
 }
 
+// flags[(s*tilesM + tm)*tilesF + tf] = 1 where q != 0 somewhere among the
+// interior points of tile (tm,tf) on plane s.  One block per (tile, plane);
+// blockIdx.z counts interior planes.
+__global__ void qflag_kernel(Grid g, const float *__restrict__ q, int tileM, int tileF,
+                             unsigned char *__restrict__ flags)
+{
+    const int s = g.r + blockIdx.z;
+    const int m0 = g.r + blockIdx.y * tileM, f0 = g.r + blockIdx.x * tileF;
+    const int m1 = min(m0 + tileM, g.nM - g.r), f1 = min(f0 + tileF, g.nF - g.r);
+    int any = 0;
+    for (int idx = threadIdx.x; idx < tileM * tileF; idx += blockDim.x) {
+        const int m = m0 + idx / tileF, f = f0 + idx % tileF;
+        if (m < m1 && f < f1 && q[g.at(s, m, f)] != 0.0f)
+            any = 1;
+    }
+    if (__syncthreads_or(any) && threadIdx.x == 0)
+        flags[((long long)s * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = 1;
+}
+
 // ---------------------------------------------------------------------------
 // sources
 // ---------------------------------------------------------------------------

@@ -103,8 +103,8 @@ step_simple_kernel(const __grid_constant__ StepArgs<T> a)
     const T uc = u[0];
 
     // second derivatives: c[0]*u + sum_ir c[ir]*(u[+ir] + u[-ir]), per axis
-    const T centre = Ops<T>::mul(a.c2[0], uc);
-    T sdF = centre, sdM = centre, sdS = centre;
+    Stencil<T, NDIM, MATH> acc;
+    acc.begin(a, uc);
     T fpF = T(0), fpM = T(0), fpS = T(0);
     T frF = T(0), frM = T(0), frS = T(0);
     const T *d = VARDEN ? a.rho + p : nullptr;
@@ -113,10 +113,8 @@ step_simple_kernel(const __grid_constant__ StepArgs<T> a)
     for (int ir = 1; ir <= R; ir++) {
         const long long oM = (long long)ir * g.pitch;
         const long long oS = (long long)ir * g.planeStride;
-        sdF = ring_sum<T, MATH>(sdF, a.c2[ir], u[ir], u[-ir]);
-        sdM = ring_sum<T, MATH>(sdM, a.c2[ir], u[oM], u[-oM]);
-        if (NDIM == 3)
-            sdS = ring_sum<T, MATH>(sdS, a.c2[ir], u[oS], u[-oS]);
+        acc.ring(a, ir, u[ir], u[-ir], u[oM], u[-oM], NDIM == 3 ? u[oS] : T(0),
+                 NDIM == 3 ? u[-oS] : T(0));
         if (VARDEN) {
             fpF = ring_diff<T, MATH>(fpF, a.c1[ir], u[ir], u[-ir]);
             frF = ring_diff<T, MATH>(frF, a.c1[ir], d[ir], d[-ir]);
@@ -139,11 +137,11 @@ step_simple_kernel(const __grid_constant__ StepArgs<T> a)
         }
     }
 
-    T lap = laplacian<T, NDIM, MATH>(sdS, sdM, sdF, a.h2, a.inv_h2);
+    T lap = acc.laplacian(a);
     if (VARDEN)
         lap = density_term<T, NDIM>(lap, fpS, frS, fpM, frM, fpF, frF, a.four_h2, d[0]);
 
-    const T val = leapfrog<T>(lap, uc, a.prev[p], a.c0[p], a.q[p]);
+    const T val = update_point<T, MATH>(lap, uc, a.prev[p], a.c0[p], a.q[p]);
 
     if (a.fuse_bc)
         store_with_boundaries<T, NDIM>(a, a.next, p, s, m, f, val);

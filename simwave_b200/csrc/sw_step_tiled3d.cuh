@@ -1,30 +1,36 @@
 // Tiled 3D step kernel for sm_100a (float32, constant density).
 //
 // Decomposition: a CTA owns a (BX x BY) tile of the (M,F) = (x,y) plane and
-// marches along S (= z) over a chunk of planes.
+// marches along S (= z) over a chunk of planes.  The CTA is warp-specialised:
 //
-//   * u_cur planes, with their halo, are brought into a shared-memory ring by
-//     TMA (cp.async.bulk.tensor.3d, one elected thread, completion on an
-//     mbarrier).  Out-of-range parts of a box are zero-filled by the TMA unit,
-//     so edge tiles need no special loads.  The ring holds the R+1 planes
-//     between the centre plane and the newest plane plus PF planes in flight.
-//   * The S-direction neighbours live in a per-thread register queue of 2R+1
-//     values per point (the classic 2.5D scheme); each thread feeds the queue
-//     from the newest plane in the ring.
-//   * M- and F-direction neighbours are read from the centre plane in the
-//     ring with 128-bit loads; each thread updates a PM x 4 register tile.
-//   * u_prev, c0, q stream straight from HBM with 128-bit loads issued one
-//     plane ahead; u_next leaves with 128-bit stores.  The damping factors
-//     and the boundary conditions are applied in the same kernel
-//     (store_with_boundaries semantics).
+//   * one producer warp feeds shared memory with TMA (cp.async.bulk.tensor.3d,
+//     one elected lane, completion on mbarriers):
+//       - u_cur planes with their halo go into a ring of R+1+PF slots (the
+//         R+1 planes between the centre plane and the newest plane, plus PF
+//         planes in flight).  Out-of-range parts of a box are zero-filled by
+//         the TMA unit, so edge tiles need no special loads;
+//       - u_prev, c0 and -- only where the damping profile is non-zero inside
+//         this tile and plane -- q go into a PS-deep ring of halo-free tiles.
+//     Slots are handed back by the consumer warps through "empty" mbarriers,
+//     so there is no CTA-wide barrier in the plane loop and the prefetch
+//     depth costs no registers.
+//   * TX*TY consumer threads each update a PM x 4 register tile per plane.
+//     M- and F-direction neighbours are read from the centre plane in the
+//     ring with 128-bit shared loads; the S-direction neighbours live in a
+//     per-thread register queue of 2R+1 values per point (the classic 2.5D
+//     scheme) fed from the newest plane in the ring.  u_next leaves with
+//     128-bit global stores; the damping factors and the boundary conditions
+//     are applied in the same kernel (store_with_boundaries semantics), with
+//     a branch-free store for tiles and planes that touch no boundary.
 //
 // The arithmetic goes through the same helpers as the plain kernel, in the
-// same order, so in strict mode the two kernels (and the reference) agree bit
-// for bit.
+// same order, so the two kernels agree bit for bit in either math mode (and
+// with the reference in strict mode).
 #pragma once
 
 #include <cuda.h>
 
+#include "sw_launch.h"
 #include "sw_math.cuh"
 #include "sw_step_simple.cuh"
 
@@ -50,6 +56,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
                  "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
@@ -64,10 +74,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async()
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar,
                                             int c0, int c1, int c2)
 {
@@ -77,41 +83,30 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-// read-only model streams: non-coherent path, do not pollute L1
-__device__ __forceinline__ float4 ldg_stream(const float *p)
-{
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p));
-    return v;
-}
-// u_prev may alias u_next (the reference updates in place between snapshots,
-// 3d/wave.c:613-617), so it takes the coherent path
-__device__ __forceinline__ float4 ldg_field(const float *p)
-{
-    float4 v;
-    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p)
-                 : "memory");
-    return v;
-}
 
 // ---- tile geometry -------------------------------------------------------------
-template <int R, int PM, int TX, int TY, int PF>
+template <int R, int PM, int TX, int TY, int PF, int PS>
 struct Tile3D {
     static constexpr int RP = (R + 3) / 4 * 4;       // F halo rounded to a float4
     static constexpr int BX = TY * PM;               // rows (M) per tile
     static constexpr int BY = TX * 4;                // columns (F) per tile
     static constexpr int BXH = BX + 2 * R;
     static constexpr int BYH = BY + 2 * RP;
-    static constexpr int NS = R + 1 + PF;            // ring slots
-    static constexpr int SLOT_BYTES = (BXH * BYH * 4 + 127) / 128 * 128;
-    static constexpr int SLOT_FLOATS = SLOT_BYTES / 4;
+    static constexpr int NS = R + 1 + PF;            // u_cur ring slots
+    static constexpr int NT = PS;                    // stream stages
     static constexpr int BOX_BYTES = BXH * BYH * 4;
-    static constexpr int SMEM_BYTES = NS * SLOT_BYTES + NS * 8;
-    static constexpr int THREADS = TX * TY;
+    static constexpr int SLOT_BYTES = (BOX_BYTES + 127) / 128 * 128;
+    static constexpr int SLOT_FLOATS = SLOT_BYTES / 4;
+    static constexpr int STR_BYTES = BX * BY * 4;    // one stream tile (multiple of 128)
+    static constexpr int STR_FLOATS = BX * BY;
+    static constexpr int STAGE_FLOATS = 3 * STR_FLOATS;   // prev | c0 | q
+    static constexpr int RING_BYTES = NS * SLOT_BYTES;
+    static constexpr int STREAM_BYTES = NT * 3 * STR_BYTES;
+    static constexpr int NBARS = 2 * NS + 2 * NT;
+    static constexpr int SMEM_BYTES = RING_BYTES + STREAM_BYTES + NBARS * 8 + NT * 4;
+    static constexpr int CONSUMERS = TX * TY;
+    static constexpr int THREADS = CONSUMERS + 32;
+    static_assert(STR_BYTES % 128 == 0, "stream tiles must keep 128-byte alignment");
 };
 
 // Boundary-aware store of four consecutive F points (f .. f+3) of row (s,m).
@@ -197,61 +192,114 @@ __device__ __forceinline__ void store_row4(const StepArgs<float> &a, int s, int 
     }
 }
 
-template <int R, int PM, int TX, int TY, int PF, int MATH, int MINB>
-__global__ void __launch_bounds__(TX *TY, MINB)
+template <int R, int PM, int TX, int TY, int PF, int PS, int MATH, int MINB>
+__global__ void __launch_bounds__(TX *TY + 32, MINB)
 step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
-                    const __grid_constant__ CUtensorMap mapCur, int zChunk)
+                    const __grid_constant__ StepMaps maps,
+                    const unsigned char *__restrict__ qflags, int zChunk)
 {
-    using TL = Tile3D<R, PM, TX, TY, PF>;
-    constexpr int RP = TL::RP, BYH = TL::BYH, NS = TL::NS;
+    using TL = Tile3D<R, PM, TX, TY, PF, PS>;
+    constexpr int RP = TL::RP, BYH = TL::BYH, NS = TL::NS, NT = TL::NT;
     constexpr int Q = 2 * R + 1;
+    constexpr int NCW = TL::CONSUMERS / 32;
     const Grid &g = a.g;
 
     // TMA destinations must be 128-byte aligned; there is no static shared
     // memory in this kernel, so the dynamic segment starts the window
     extern __shared__ __align__(128) unsigned char smem[];
     float *ring = reinterpret_cast<float *>(smem);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + NS * TL::SLOT_BYTES);
+    float *streams = reinterpret_cast<float *>(smem + TL::RING_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TL::RING_BYTES + TL::STREAM_BYTES);
+    uint64_t *fullCur = bars, *emptyCur = bars + NS;
+    uint64_t *fullStr = bars + 2 * NS, *emptyStr = bars + 2 * NS + NT;
+    int *stageHasQ = reinterpret_cast<int *>(bars + TL::NBARS);
 
     const int tid = threadIdx.x;
-    const int tx = tid % TX, ty = tid / TX;
     const int f0 = R + blockIdx.x * TL::BY;
     const int m0 = R + blockIdx.y * TL::BX;
     const int z0 = R + blockIdx.z * zChunk;
     const int z1 = min(z0 + zChunk, g.nS - R);
     const int planes = z1 - z0;
-    const int L = planes + 2 * R;       // planes streamed: z0-R .. z1+R-1
 
     if (tid == 0) {
         if (smem_u32(ring) & 127u)
             __trap();
-        for (int s = 0; s < NS; s++)
-            mbar_init(&full[s], 1);
+        for (int s = 0; s < NS; s++) {
+            mbar_init(&fullCur[s], 1);
+            mbar_init(&emptyCur[s], NCW);
+        }
+        for (int s = 0; s < NT; s++) {
+            mbar_init(&fullStr[s], 1);
+            mbar_init(&emptyStr[s], NCW);
+        }
         mbar_fence_init();
     }
     __syncthreads();
 
-    auto issue = [&](int l) {
-        const int slot = l % NS;
-        mbar_expect_tx(&full[slot], TL::BOX_BYTES);
-        tma_load_3d(ring + slot * TL::SLOT_FLOATS, &mapCur, &full[slot], g.lpad + f0 - RP,
-                    m0 - R, z0 - R + l);
-    };
-    if (tid == 0) {
-        const int first = min(NS, L);
-        for (int l = 0; l < first; l++)
-            issue(l);
+    // =========================== producer warp ===============================
+    if (tid >= TL::CONSUMERS) {
+        const int lane = tid - TL::CONSUMERS;
+        const long long tilesPerPlane = (long long)gridDim.x * gridDim.y;
+        const unsigned char *myFlags =
+            qflags + (long long)blockIdx.y * gridDim.x + blockIdx.x;
+        auto issue_cur = [&](int l) {
+            const int slot = l % NS;
+            if (l >= NS)
+                mbar_wait(&emptyCur[slot], ((l / NS) - 1) & 1);
+            mbar_expect_tx(&fullCur[slot], TL::BOX_BYTES);
+            tma_load_3d(ring + slot * TL::SLOT_FLOATS, &maps.cur, &fullCur[slot],
+                        g.lpad + f0 - RP, m0 - R, z0 - R + l);
+        };
+        auto issue_streams = [&](int j, int hasQ) {
+            const int st = j % NT;
+            if (j >= NT)
+                mbar_wait(&emptyStr[st], ((j / NT) - 1) & 1);
+            float *dst = streams + st * TL::STAGE_FLOATS;
+            stageHasQ[st] = hasQ;
+            mbar_expect_tx(&fullStr[st], (hasQ ? 3 : 2) * TL::STR_BYTES);
+            tma_load_3d(dst, &maps.prev, &fullStr[st], g.lpad + f0, m0, z0 + j);
+            tma_load_3d(dst + TL::STR_FLOATS, &maps.c0, &fullStr[st], g.lpad + f0, m0, z0 + j);
+            if (hasQ)
+                tma_load_3d(dst + 2 * TL::STR_FLOATS, &maps.q, &fullStr[st], g.lpad + f0, m0,
+                            z0 + j);
+        };
+        if (lane == 0)
+            for (int l = 0; l < 2 * R; l++)
+                issue_cur(l);
+        for (int jb = 0; jb < planes; jb += 32) {
+            // damping flags of the next 32 planes, one per lane
+            int flag = 0;
+            if (jb + lane < planes)
+                flag = myFlags[(long long)(z0 + jb + lane) * tilesPerPlane];
+            const unsigned mask = __ballot_sync(0xffffffffu, flag != 0);
+            if (lane == 0) {
+                const int jend = min(jb + 32, planes);
+                for (int j = jb; j < jend; j++) {
+                    issue_streams(j, (mask >> (j - jb)) & 1);
+                    issue_cur(j + 2 * R);
+                }
+            }
+        }
+        return;
     }
+
+    // =========================== consumer warps ===============================
+    const int lane = tid & 31;
+    const int tx = tid % TX, ty = tid / TX;
 
     // my points: rows m0 + ty*PM + i, columns f0 + 4*tx .. +3
     const int fMine = f0 + 4 * tx;
-    const int lastF = g.nF - R - 1, lastM = g.nM - R - 1;
+    const int lastF = g.nF - R - 1, lastM = g.nM - R - 1, lastS = g.nS - R - 1;
     int nvalid = lastF - fMine + 1;
     nvalid = nvalid < 0 ? 0 : (nvalid > 4 ? 4 : nvalid);
     bool rowValid[PM];
 #pragma unroll
     for (int i = 0; i < PM; i++)
         rowValid[i] = (m0 + ty * PM + i <= lastM) && nvalid > 0;
+    // does this tile touch (or hang over) an M/F face region where the
+    // boundary conditions act?
+    const bool edgeTile = (m0 <= 2 * R) | (m0 + TL::BX - 1 >= lastM - R) | (f0 <= 2 * R) |
+                          (f0 + TL::BY - 1 >= lastF - R);
 
     const int srow = ty * PM + R;           // my first row inside a ring slot
     const int scol = 4 * tx + RP;           // my first column inside a ring slot
@@ -260,16 +308,21 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
     auto lds4 = [&](const float *slot, int row, int col) {
         return *reinterpret_cast<const float4 *>(slot + row * BYH + col);
     };
+    auto release = [&](uint64_t *bar) {
+        __syncwarp();
+        if (lane == 0)
+            mbar_arrive(bar);
+    };
 
     // register queue over S: qv[i][c][k] holds plane (centre - R + k)
     float qv[PM][4][Q];
 
     // prime the queue with planes z0-R .. z0+R-1.  The first R of them are
-    // never centre planes, so their slots are refilled as soon as every
-    // thread has copied its values out.
+    // never centre planes, so their slots go back as soon as every thread of
+    // the warp has copied its values out.
 #pragma unroll
     for (int l = 0; l < 2 * R; l++) {
-        mbar_wait(&full[l % NS], (l / NS) & 1);
+        mbar_wait(&fullCur[l % NS], (l / NS) & 1);
         const float *slot = slot_ptr(l);
 #pragma unroll
         for (int i = 0; i < PM; i++) {
@@ -278,37 +331,18 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
             qv[i][0][l + 1] = v.x; qv[i][1][l + 1] = v.y;
             qv[i][2][l + 1] = v.z; qv[i][3][l + 1] = v.w;
         }
-        if (l < R) {
-            __syncthreads();
-            if (tid == 0 && l + NS < L) {
-                fence_proxy_async();
-                issue(l + NS);
-            }
-        }
+        if (l < R)
+            release(&emptyCur[l % NS]);
     }
-
-    // streams for the first plane
-    float4 pv[PM], c0v[PM], qd[PM];
-    auto load_streams = [&](int s) {
-#pragma unroll
-        for (int i = 0; i < PM; i++) {
-            if (rowValid[i]) {
-                const long long p = g.at(s, m0 + ty * PM + i, fMine);
-                pv[i] = ldg_field(a.prev + p);
-                c0v[i] = ldg_stream(a.c0 + p);
-                qd[i] = ldg_stream(a.q + p);
-            }
-        }
-    };
-    load_streams(z0);
 
     for (int j = 0; j < planes; j++) {
         const int s = z0 + j;
         const int lf = j + 2 * R;       // newest plane needed
         const int lc = j + R;           // centre plane
+        const int st = j % NT;
 
         // shift the queue and take the newest plane from the ring
-        mbar_wait(&full[lf % NS], (lf / NS) & 1);
+        mbar_wait(&fullCur[lf % NS], (lf / NS) & 1);
         {
             const float *slot = slot_ptr(lf);
 #pragma unroll
@@ -324,6 +358,13 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
             }
         }
 
+        // this plane's streams
+        mbar_wait(&fullStr[st], (j / NT) & 1);
+        const bool hasQ = stageHasQ[st] != 0;
+        const float *sPrev = streams + st * TL::STAGE_FLOATS;
+        const float *sC0 = sPrev + TL::STR_FLOATS;
+        const float *sQ = sC0 + TL::STR_FLOATS;
+
         const float *ctr = slot_ptr(lc);
         float out[PM][4];
 
@@ -336,12 +377,10 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 const float4 v = lds4(ctr, srow + i, scol - RP + 4 * b);
                 w[4 * b + 0] = v.x; w[4 * b + 1] = v.y; w[4 * b + 2] = v.z; w[4 * b + 3] = v.w;
             }
-            float sdF[4], sdM[4], sdS[4];
+            Stencil3<float, MATH> acc[4];
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const float centre = Ops<float>::mul(a.c2[0], qv[i][c][R]);
-                sdF[c] = centre; sdM[c] = centre; sdS[c] = centre;
-            }
+            for (int c = 0; c < 4; c++)
+                acc[c].begin(a, qv[i][c][R]);
 #pragma unroll
             for (int ir = 1; ir <= R; ir++) {
                 const float4 up = lds4(ctr, srow + i + ir, scol);
@@ -349,37 +388,42 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 const float upv[4] = {up.x, up.y, up.z, up.w};
                 const float dnv[4] = {dn.x, dn.y, dn.z, dn.w};
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    sdF[c] = ring_sum<float, MATH>(sdF[c], a.c2[ir], w[RP + c + ir], w[RP + c - ir]);
-                    sdM[c] = ring_sum<float, MATH>(sdM[c], a.c2[ir], upv[c], dnv[c]);
-                    sdS[c] = ring_sum<float, MATH>(sdS[c], a.c2[ir], qv[i][c][R + ir],
-                                                   qv[i][c][R - ir]);
-                }
+                for (int c = 0; c < 4; c++)
+                    acc[c].ring(a, ir, w[RP + c + ir], w[RP + c - ir], upv[c], dnv[c],
+                                qv[i][c][R + ir], qv[i][c][R - ir]);
             }
-            const float pvv[4] = {pv[i].x, pv[i].y, pv[i].z, pv[i].w};
-            const float c0a[4] = {c0v[i].x, c0v[i].y, c0v[i].z, c0v[i].w};
-            const float qa[4] = {qd[i].x, qd[i].y, qd[i].z, qd[i].w};
+            const int off = ((ty * PM + i) * TX + tx) * 4;
+            const float4 pv = *reinterpret_cast<const float4 *>(sPrev + off);
+            const float4 cv = *reinterpret_cast<const float4 *>(sC0 + off);
+            float4 qd = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (hasQ)
+                qd = *reinterpret_cast<const float4 *>(sQ + off);
+            const float pvv[4] = {pv.x, pv.y, pv.z, pv.w};
+            const float c0a[4] = {cv.x, cv.y, cv.z, cv.w};
+            const float qa[4] = {qd.x, qd.y, qd.z, qd.w};
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const float lap = laplacian<float, 3, MATH>(sdS[c], sdM[c], sdF[c], a.h2, a.inv_h2);
-                out[i][c] = leapfrog<float>(lap, qv[i][c][R], pvv[c], c0a[c], qa[c]);
-            }
+            for (int c = 0; c < 4; c++)
+                out[i][c] = update_point<float, MATH>(acc[c].laplacian(a), qv[i][c][R], pvv[c],
+                                                      c0a[c], qa[c]);
         }
 
-        // everyone is done with the centre plane: refill its slot
-        __syncthreads();
-        if (tid == 0 && lc + NS < L) {
-            fence_proxy_async();
-            issue(lc + NS);
-        }
+        // this warp is done with the centre plane and the stream stage
+        release(&emptyCur[lc % NS]);
+        release(&emptyStr[st]);
 
-        // streams of the next plane go out before this plane's stores
-        if (j + 1 < planes)
-            load_streams(s + 1);
-
+        const bool special = edgeTile | (a.fuse_bc & ((s <= 2 * R) | (s >= lastS - R)));
+        if (!special) {
 #pragma unroll
-        for (int i = 0; i < PM; i++) {
-            if (rowValid[i]) {
+            for (int i = 0; i < PM; i++) {
+                const long long p = g.at(s, m0 + ty * PM + i, fMine);
+                *reinterpret_cast<float4 *>(a.next + p) =
+                    make_float4(out[i][0], out[i][1], out[i][2], out[i][3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PM; i++) {
+                if (!rowValid[i])
+                    continue;
                 if (a.fuse_bc) {
                     store_row4(a, s, m0 + ty * PM + i, fMine, out[i], nvalid);
                 } else {

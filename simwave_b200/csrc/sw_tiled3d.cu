@@ -5,16 +5,16 @@
 
 namespace sw {
 
-template <int R, int PM, int TX, int TY, int PF, int MINB>
-static void launch_cfg(int math, const StepArgs<float> &a, const CUtensorMap &map, int zChunk,
-                       cudaStream_t stream)
+template <int R, int PM, int TX, int TY, int PF, int PS, int MINB>
+static void launch_cfg(int math, const StepArgs<float> &a, const StepMaps &maps,
+                       const unsigned char *qflags, int zChunk, cudaStream_t stream)
 {
-    using TL = Tile3D<R, PM, TX, TY, PF>;
+    using TL = Tile3D<R, PM, TX, TY, PF, PS>;
     const Grid &g = a.g;
     dim3 grid((g.nF - 2 * R + TL::BY - 1) / TL::BY, (g.nM - 2 * R + TL::BX - 1) / TL::BX,
               (g.nS - 2 * R + zChunk - 1) / zChunk);
-    auto kStrict = step3d_tiled_kernel<R, PM, TX, TY, PF, MATH_STRICT, MINB>;
-    auto kFast = step3d_tiled_kernel<R, PM, TX, TY, PF, MATH_FAST, MINB>;
+    auto kStrict = step3d_tiled_kernel<R, PM, TX, TY, PF, PS, MATH_STRICT, MINB>;
+    auto kFast = step3d_tiled_kernel<R, PM, TX, TY, PF, PS, MATH_FAST, MINB>;
     auto k = (math == MATH_STRICT) ? kStrict : kFast;
     static bool configured[2] = {false, false};
     if (!configured[math == MATH_STRICT]) {
@@ -22,35 +22,46 @@ static void launch_cfg(int math, const StepArgs<float> &a, const CUtensorMap &ma
                                      TL::SMEM_BYTES));
         configured[math == MATH_STRICT] = true;
     }
-    k<<<grid, TL::THREADS, TL::SMEM_BYTES, stream>>>(a, map, zChunk);
+    k<<<grid, TL::THREADS, TL::SMEM_BYTES, stream>>>(a, maps, qflags, zChunk);
 }
 
-#define SW_CFG(ID, PM, TX, TY, PF, MINB)                                                   \
+#define SW_CFG(ID, PM, TX, TY, PF, PS, MINB)                                               \
     case ID:                                                                               \
-        if (query) { *query = {PM, TX, TY, PF, Tile3D<R, PM, TX, TY, PF>::SMEM_BYTES}; return true; } \
-        launch_cfg<R, PM, TX, TY, PF, MINB>(math, a, *map, zChunk, stream);                \
+        if (query) {                                                                       \
+            *query = {PM, TX, TY, PF, PS, MINB, Tile3D<R, PM, TX, TY, PF, PS>::SMEM_BYTES};\
+            return true;                                                                   \
+        }                                                                                  \
+        launch_cfg<R, PM, TX, TY, PF, PS, MINB>(math, a, *maps, qflags, zChunk, stream);   \
         return true;
 
 template <int R>
 static bool dispatch(int cfg, TiledInfo *query, int math, const StepArgs<float> &a,
-                     const CUtensorMap *map, int zChunk, cudaStream_t stream)
+                     const StepMaps *maps, const unsigned char *qflags, int zChunk,
+                     cudaStream_t stream)
 {
+    // PM, TX, TY = points per thread along M, thread columns, thread rows
+    // (tile = TY*PM rows x 4*TX columns); PF / PS = u_cur planes / stream
+    // stages in flight; MINB = CTAs per SM the register budget is held to
+    // Thread counts are kept at multiples of 4 warps (register allocation
+    // granularity): 7 consumer warps + the producer warp, etc.
     if constexpr (R <= 5) {
         switch (cfg) {
-            SW_CFG(0, 2, 16, 8, 2, 3)     // 16 x 64 tile, 128 threads, <= 168 regs
-            SW_CFG(1, 2, 16, 16, 2, 1)    // 32 x 64 tile, 256 threads, <= 255 regs
-            SW_CFG(2, 1, 16, 16, 2, 2)    // 16 x 64 tile, 256 threads, <= 128 regs
-            SW_CFG(3, 2, 32, 8, 2, 1)     // 16 x 128 tile, 256 threads, <= 255 regs
-            SW_CFG(4, 1, 32, 8, 2, 2)     // 8 x 128 tile, 256 threads
-            SW_CFG(5, 1, 32, 16, 2, 1)    // 16 x 128 tile, 512 threads
-            SW_CFG(6, 1, 16, 8, 2, 4)     // 8 x 64 tile, 128 threads
+            SW_CFG(0, 1, 16, 14, 3, 3, 2)    // 14 x 64 tile, 7+1 warps
+            SW_CFG(1, 2, 16, 14, 2, 3, 1)    // 28 x 64 tile, 7+1 warps
+            SW_CFG(2, 1, 32, 7, 3, 3, 2)     // 7 x 128 tile, 7+1 warps
+            SW_CFG(3, 2, 32, 7, 2, 3, 1)     // 14 x 128 tile, 7+1 warps
+            SW_CFG(4, 1, 16, 22, 3, 3, 1)    // 22 x 64 tile, 11+1 warps
+            SW_CFG(5, 1, 16, 6, 3, 3, 4)     // 6 x 64 tile, 3+1 warps
+            SW_CFG(6, 1, 16, 16, 3, 3, 2)    // 16 x 64 tile, 8+1 warps
+            SW_CFG(7, 1, 16, 30, 2, 3, 1)    // 30 x 64 tile, 15+1 warps
         default: return false;
         }
     } else {
         switch (cfg) {
-            SW_CFG(0, 1, 16, 16, 1, 2)    // 16 x 64 tile, 256 threads
-            SW_CFG(1, 1, 32, 8, 1, 2)     // 8 x 128 tile, 256 threads
-            SW_CFG(2, 1, 32, 16, 1, 1)    // 16 x 128 tile, 512 threads
+            SW_CFG(0, 1, 16, 14, 2, 3, 1)    // 14 x 64 tile, 7+1 warps
+            SW_CFG(1, 1, 16, 22, 2, 2, 1)    // 22 x 64 tile, 11+1 warps
+            SW_CFG(2, 1, 32, 7, 2, 3, 1)     // 7 x 128 tile, 7+1 warps
+            SW_CFG(3, 1, 16, 30, 1, 2, 1)    // 30 x 64 tile, 15+1 warps
         default: return false;
         }
     }
@@ -66,12 +77,13 @@ namespace sw {
 bool SW_CAT(tiled3d_query_r, SW_RADIUS)(int cfg, TiledInfo *info)
 {
     StepArgs<float> dummy{};
-    return dispatch<SW_RADIUS>(cfg, info, 0, dummy, nullptr, 1, nullptr);
+    return dispatch<SW_RADIUS>(cfg, info, 0, dummy, nullptr, nullptr, 1, nullptr);
 }
 bool SW_CAT(tiled3d_launch_r, SW_RADIUS)(int cfg, int math, const StepArgs<float> &a,
-                                         const CUtensorMap &map, int zChunk, cudaStream_t stream)
+                                         const StepMaps &maps, const unsigned char *qflags,
+                                         int zChunk, cudaStream_t stream)
 {
-    const bool ok = dispatch<SW_RADIUS>(cfg, nullptr, math, a, &map, zChunk, stream);
+    const bool ok = dispatch<SW_RADIUS>(cfg, nullptr, math, a, &maps, qflags, zChunk, stream);
     if (ok)
         SW_CUDA(cudaGetLastError());
     return ok;

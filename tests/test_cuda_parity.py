@@ -4,10 +4,15 @@ GPU parity tests proper: the CUDA backend, called through the drop-in C ABI
 inputs, and against the golden vectors of the unmodified reference.
 
 Tolerances (float32, from BASELINE.md / SURVEY.md section 8d):
-  * strict math mode (default): the arithmetic is rounded exactly where the
-    reference rounds it, so wavefield and receivers are required to be
-    BIT-IDENTICAL to the sequential C oracle;
-  * fast math mode: relative L2 <= 1e-5 for runs of <= 500 steps.
+  * default ("fast") math mode: relative L2 <= 1e-5 for runs of <= 500 steps
+    (the north star's stated float32 tolerance); float64 <= 1e-12;
+  * strict math mode (SIMWAVE_CUDA_MATH=strict): the arithmetic is rounded
+    exactly where the reference rounds it, so wavefield and receivers are
+    required to be BIT-IDENTICAL to the sequential C oracle.
+Most tests below run in strict mode (autouse fixture) because bit identity is
+the sharpest check of the loop structure, boundary logic, source ordering and
+snapshot plumbing; the *_default_math tests repeat the sweep in the default
+mode against the tolerance.
 """
 import os
 import sys
@@ -28,6 +33,19 @@ from conftest import rel_l2  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 REL_L2_TOL = 1e-5   # float32, <= 500 steps (north star / BASELINE.md section 3)
+REL_L2_TOL_F64 = 1e-12
+
+
+@pytest.fixture(autouse=True)
+def strict_math(monkeypatch):
+    monkeypatch.setenv("SIMWAVE_CUDA_MATH", "strict")
+
+
+def assert_close(a, b, dtype=np.float32):
+    tol = REL_L2_TOL if np.dtype(dtype) == np.float32 else REL_L2_TOL_F64
+    assert np.abs(a["u"]).max() > 0
+    eu, er = rel_l2(b["u"], a["u"]), rel_l2(b["receivers"], a["receivers"])
+    assert eu <= tol and er <= tol, (eu, er)
 
 
 def run_pair(p, env=None, monkeypatch=None):
@@ -81,6 +99,22 @@ def test_strict_mode_bit_identical_to_oracle(shape, order, density, dtype,
         rec_radius=2, multi_wavelet=(stride % 2 == 0), seed=order + stride)
     a, b = run_pair(p)
     assert_identical(a, b)
+
+
+@pytest.mark.parametrize("shape,order,density,dtype,stride,steps,bc", ABI_CASES)
+def test_default_math_within_tolerance(shape, order, density, dtype, stride,
+                                       steps, bc, monkeypatch):
+    ndim = len(shape)
+    r = order // 2
+    nbl = tuple((0, 3) if a == 0 else (2, 4) for a in range(ndim))
+    p = problems.make_problem(
+        shape=shape, space_order=order, density=density, dtype=dtype,
+        timesteps=steps, saving_stride=stride, nbl=nbl, bc=bc,
+        num_sources=3, num_receivers=9, src_radius=min(4, r + 1),
+        rec_radius=2, multi_wavelet=(stride % 2 == 0), seed=order + stride)
+    monkeypatch.delenv("SIMWAVE_CUDA_MATH")
+    a, b = run_pair(p)
+    assert_close(a, b, dtype)
 
 
 @pytest.mark.parametrize("ndim", [2, 3])
@@ -139,14 +173,17 @@ def test_tiny_grid_takes_separate_boundary_path():
     assert_identical(a, b)
 
 
-@pytest.mark.parametrize("shape,order,density", [
-    ((60, 64), 8, False), ((40, 44, 48), 8, False), ((36, 36, 36), 4, True)])
-def test_fast_math_within_tolerance(shape, order, density, monkeypatch):
+@pytest.mark.parametrize("shape,order,density,steps", [
+    ((60, 64), 8, False, 60), ((40, 44, 48), 8, False, 60),
+    ((36, 36, 36), 4, True, 60), ((120, 130), 8, False, 500),
+    ((70, 150, 140), 8, False, 300), ((48, 50, 52), 16, True, 200)])
+def test_fast_math_within_tolerance(shape, order, density, steps, monkeypatch):
+    nbl = ((0, 6),) + ((5, 5),) * (len(shape) - 1)
     p = problems.make_problem(shape=shape, space_order=order, density=density,
-                              timesteps=60, seed=3, smooth_density=True)
+                              timesteps=steps, seed=3, smooth_density=True,
+                              nbl=nbl)
     a, b = run_pair(p, {"SIMWAVE_CUDA_MATH": "fast"}, monkeypatch)
-    assert rel_l2(b["u"], a["u"]) <= REL_L2_TOL
-    assert rel_l2(b["receivers"], a["receivers"]) <= REL_L2_TOL
+    assert_close(a, b)
 
 
 def test_nonzero_initial_fields_are_honoured():
@@ -189,6 +226,35 @@ def test_small_cases_match_reference_golden(golden, name):
     u, recv = solver.forward()
     assert np.array_equal(recv, ref[name + "/recv"])
     assert np.array_equal(u[ref[name + "/u_idx"]], ref[name + "/u"])
+
+
+@pytest.mark.parametrize("dimension,space_order,density", [
+    (2, 2, False), (2, 8, False), (3, 2, False), (3, 8, False),
+    (2, 2, True), (3, 2, True)])
+def test_solution_default_math(golden, dimension, space_order, density,
+                               monkeypatch):
+    """Reference tests/test_solution.py with language='cuda' in the default
+    math mode: the reference's CPU bar, np.allclose(atol=1e-5)
+    (tests/test_solution.py:139), tighter than its own GPU bar (atol=1e-4,
+    tests/test_gpu_solution.py:139)."""
+    monkeypatch.delenv("SIMWAVE_CUDA_MATH")
+    ref = golden("solution_%dd_so%d" % (dimension, space_order))
+    solver = cases.solution_solver(api, dimension, space_order,
+                                   api.Compiler(**CUDA), density=density)
+    u, recv = solver.forward()
+    if dimension == 2:
+        assert np.allclose(u, ref["u_reference_npy"], atol=1e-5)
+        assert np.allclose(u, ref["u"], atol=1e-5)
+        assert rel_l2(u, ref["u"]) <= REL_L2_TOL
+        if not density:
+            assert rel_l2(recv, ref["recv"]) <= REL_L2_TOL
+    else:
+        f = u[0]
+        c = [n // 2 for n in f.shape]
+        planes = (f[c[0]], f[:, c[1]], f[:, :, c[2]])
+        for got, key in zip(planes, ("plane_z", "plane_x", "plane_y")):
+            assert np.allclose(got, ref[key], atol=1e-5)
+            assert rel_l2(got, ref[key]) <= REL_L2_TOL
 
 
 @pytest.mark.parametrize("dimension,space_order,density", [
@@ -274,15 +340,17 @@ def _tiled_vs_plain(order, tile, monkeypatch, shape=(37, 75, 150), steps=6,
     return plain, tiled
 
 
+@pytest.mark.parametrize("math", ["strict", "fast"])
 @pytest.mark.parametrize("order", [2, 4, 6, 8, 10, 12, 14, 16, 18, 20])
-def test_tiled_kernel_every_radius(order, monkeypatch):
-    for cfg in (0, 1, 2):
-        plain, tiled = _tiled_vs_plain(order, "%d:11" % cfg, monkeypatch)
+def test_tiled_kernel_every_radius(order, math, monkeypatch):
+    for cfg in (0, 1, 2, 3):
+        plain, tiled = _tiled_vs_plain(order, "%d:11" % cfg, monkeypatch,
+                                       math=math)
         assert np.array_equal(plain["u"], tiled["u"]), (order, cfg)
         assert np.array_equal(plain["receivers"], tiled["receivers"])
 
 
-@pytest.mark.parametrize("cfg", range(7))
+@pytest.mark.parametrize("cfg", range(8))
 @pytest.mark.parametrize("bc", [(2, 2, 2, 2, 2, 2), (1, 1, 1, 1, 1, 1),
                                 (0, 2, 1, 0, 2, 1)])
 def test_tiled_kernel_every_configuration(cfg, bc, monkeypatch):
@@ -293,8 +361,10 @@ def test_tiled_kernel_every_configuration(cfg, bc, monkeypatch):
 
 
 def test_tiled_kernel_fast_math_matches_plain_fast_math(monkeypatch):
-    plain, tiled = _tiled_vs_plain(8, "2:0", monkeypatch, math="fast")
-    assert rel_l2(tiled["u"], plain["u"]) <= 1e-6
+    for cfg in range(8):
+        plain, tiled = _tiled_vs_plain(8, "%d:0" % cfg, monkeypatch,
+                                       math="fast", steps=12)
+        assert np.array_equal(tiled["u"], plain["u"]), cfg
 
 
 def test_tiled_kernel_in_place_between_snapshots(monkeypatch):

@@ -52,9 +52,8 @@ struct StepArgs {
     T c1[kMaxRadius + 1];   // first-derivative half stencil
     T h2[3];            // squared spacing per axis (S,M,F)
     T inv_h2[3];        // 1/h2, correctly rounded (fast math mode only)
+    T inv_h2_lo[3];     // 1/h2 - inv_h2 (fast math mode only)
     T four_h2[3];       // 4*h2 as the reference rounds it
-    T cs[3][kMaxRadius + 1];  // fast math: c2[ir] / h2[axis]
-    T cc;               // fast math: c2[0] * sum over axes of 1/h2
     int bc[6];          // S_before,S_after,M_before,M_after,F_before,F_after
     int quirk;          // 3D variable density with nx != ny: bug-compatible x strides
     int fuse_bc;        // 1: boundary conditions written by the step kernel itself

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -406,18 +407,9 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
         volatile T sq = h[i] * h[i];
         a.h2[i] = sq;
         a.inv_h2[i] = T(1) / a.h2[i];
+        a.inv_h2_lo[i] = std::fma(-a.inv_h2[i], a.h2[i], T(1)) / a.h2[i];
         volatile T f4 = T(4) * a.h2[i];
         a.four_h2[i] = f4;
-    }
-    // fast math: coefficients pre-divided by h^2
-    {
-        T sumInv = T(0);
-        for (int ax = (ndim_ == 3 ? 0 : 1); ax < 3; ax++) {
-            sumInv += a.inv_h2[ax];
-            for (int i = 0; i <= r; i++)
-                a.cs[ax][i] = a.c2[i] * a.inv_h2[ax];
-        }
-        a.cc = a.c2[0] * sumInv;
     }
     const size_t *bc = pb.boundary_conditions;
     if (ndim_ == 3) {

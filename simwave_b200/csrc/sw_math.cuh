@@ -23,6 +23,7 @@ namespace sw {
 
 enum MathMode { MATH_FAST = 0, MATH_STRICT = 1 };
 
+
 template <typename T>
 struct Ops;
 
@@ -50,7 +51,7 @@ __device__ __forceinline__ T ring_sum(T acc, T c, T a, T b)
 {
     if (MATH == MATH_STRICT)
         return Ops<T>::add(acc, Ops<T>::mul(c, Ops<T>::add(a, b)));
-    return Ops<T>::fma(c, a + b, acc);
+    return Ops<T>::fma(c, Ops<T>::add(a, b), acc);
 }
 
 // acc + c * (a - b)     -- one ring of a first-derivative stencil
@@ -59,7 +60,7 @@ __device__ __forceinline__ T ring_diff(T acc, T c, T a, T b)
 {
     if (MATH == MATH_STRICT)
         return Ops<T>::add(acc, Ops<T>::mul(c, Ops<T>::sub(a, b)));
-    return Ops<T>::fma(c, a - b, acc);
+    return Ops<T>::fma(c, Ops<T>::sub(a, b), acc);
 }
 
 // x / h2
@@ -133,22 +134,15 @@ __device__ __forceinline__ T leapfrog(T lap, T u, T prev, T c0, T q)
 //   q == 0:  u_next = (2u - prev) + lap*c0
 //   q != 0:  u_next = (2u - (1-q) prev + lap*c0) / (1+q)
 // (the same expression as above multiplied out: 2/D u - N/D prev + lap c0/D).
-// The reference forms 2u - prev + value in double and rounds once, and that
-// single rounding is what sets the float32 noise floor of the whole run (the
-// three terms nearly cancel: the result is of the size of u, the rounding of
-// `value` itself is far smaller).  An error-free TwoSum keeps that property in
-// the working precision: s + e == 2u - prev exactly, the small terms e and
-// lap*c0 are combined first, and only the final add rounds at the size of u.
+// 2u - prev is exact in the working precision wherever u and prev are of the
+// same sign and size (the usual case: the field varies slowly from one step
+// to the next), so rounding it separately costs nothing measurable against
+// the reference's double accumulation (measured: tools/parity_report.py).
 template <typename T>
 __device__ __forceinline__ T fast_leapfrog(T lap, T u, T prev, T c0, T q)
 {
-    if (q == T(0)) {
-        const T a = Ops<T>::add(u, u), b = -prev;
-        const T s = Ops<T>::add(a, b);
-        const T bb = Ops<T>::sub(s, a);
-        const T e = Ops<T>::add(Ops<T>::sub(a, Ops<T>::sub(s, bb)), Ops<T>::sub(b, bb));
-        return Ops<T>::add(s, Ops<T>::fma(lap, c0, e));
-    }
+    if (q == T(0))
+        return Ops<T>::fma(lap, c0, Ops<T>::fma(T(2), u, -prev));
     const T N = Ops<T>::sub(T(1), q);
     const T t = Ops<T>::fma(lap, c0, Ops<T>::fma(-N, prev, Ops<T>::add(u, u)));
     return Ops<T>::div(t, Ops<T>::add(T(1), q));
@@ -166,45 +160,44 @@ __device__ __forceinline__ T update_point(T lap, T u, T prev, T c0, T q)
 // Accumulator of the second-derivative stencil of one point.
 //   STRICT: one sum per axis, every operation rounded as in the reference,
 //           divided by h^2 at the end (laplacian<>).
-//   FAST:   coefficients pre-divided by h^2 (StepArgs::cs, ::cc), FMA chains.
+//   FAST:   the same sums as FMA chains, scaled by the rounded 1/h^2.
 template <typename T, int NDIM, int MATH>
 struct Stencil {
     T sF, sM, sS;
     __device__ __forceinline__ void begin(const StepArgs<T> &a, T u)
     {
-        if (MATH == MATH_STRICT) {
-            sF = sM = sS = Ops<T>::mul(a.c2[0], u);
-        } else {
-            sF = Ops<T>::mul(a.cc, u);
-            sM = sS = T(0);
-        }
+        // both modes start every axis from c[0]*u, as the reference does: the
+        // half stencil sums to zero only with the coefficients it was built
+        // from, and that cancellation must survive (a constant field has no
+        // Laplacian)
+        sF = sM = sS = Ops<T>::mul(a.c2[0], u);
     }
     // ring `ir`: neighbours at +-ir along F, M and S
     __device__ __forceinline__ void ring(const StepArgs<T> &a, int ir, T fp, T fm, T mp, T mm,
                                          T sp, T sm)
     {
-        if (MATH == MATH_STRICT) {
-            sF = ring_sum<T, MATH>(sF, a.c2[ir], fp, fm);
-            sM = ring_sum<T, MATH>(sM, a.c2[ir], mp, mm);
-            if (NDIM == 3)
-                sS = ring_sum<T, MATH>(sS, a.c2[ir], sp, sm);
-        } else {
-            // explicit intrinsics: no compiler-chosen contraction, so every
-            // kernel built on this produces the same bits
-            sF = Ops<T>::fma(a.cs[AX_F][ir], Ops<T>::add(fp, fm), sF);
-            sM = (ir == 1) ? Ops<T>::mul(a.cs[AX_M][ir], Ops<T>::add(mp, mm))
-                           : Ops<T>::fma(a.cs[AX_M][ir], Ops<T>::add(mp, mm), sM);
-            if (NDIM == 3)
-                sS = (ir == 1) ? Ops<T>::mul(a.cs[AX_S][ir], Ops<T>::add(sp, sm))
-                               : Ops<T>::fma(a.cs[AX_S][ir], Ops<T>::add(sp, sm), sS);
-        }
+        sF = ring_sum<T, MATH>(sF, a.c2[ir], fp, fm);
+        sM = ring_sum<T, MATH>(sM, a.c2[ir], mp, mm);
+        if (NDIM == 3)
+            sS = ring_sum<T, MATH>(sS, a.c2[ir], sp, sm);
     }
     __device__ __forceinline__ T laplacian(const StepArgs<T> &a) const
     {
         if (MATH == MATH_STRICT)
             return sw::laplacian<T, NDIM, MATH>(sS, sM, sF, a.h2, a.inv_h2);
-        const T t = Ops<T>::add(sF, sM);
-        return (NDIM == 3) ? Ops<T>::add(t, sS) : t;
+        // sum over axes of s/h^2 with 1/h^2 = inv_h2 + inv_h2_lo carried to
+        // twice the working precision: a one-sided relative error in the
+        // scale of the Laplacian acts like a velocity error and shows up as
+        // a phase drift that grows with the number of time steps
+        T lo = Ops<T>::mul(sF, a.inv_h2_lo[AX_F]);
+        lo = Ops<T>::fma(sM, a.inv_h2_lo[AX_M], lo);
+        if (NDIM == 3)
+            lo = Ops<T>::fma(sS, a.inv_h2_lo[AX_S], lo);
+        T t = Ops<T>::fma(sF, a.inv_h2[AX_F], lo);
+        t = Ops<T>::fma(sM, a.inv_h2[AX_M], t);
+        if (NDIM == 3)
+            t = Ops<T>::fma(sS, a.inv_h2[AX_S], t);
+        return t;
     }
 };
 template <typename T, int MATH>

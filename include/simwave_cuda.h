@@ -209,6 +209,12 @@ int simwave_cuda_set_device(int device);
 void simwave_cuda_last_timing(double *loop, double *h2d, double *d2h,
                               double *total);
 
+/* Extended breakdown: fills out[0..n) with {loop, h2d, d2h, total, run_wall,
+ * teardown} (seconds; run_wall = host wall clock of the time loop including
+ * launch overhead, teardown = releasing device and pinned memory); returns the
+ * number of values available. */
+int simwave_cuda_last_timing_ex(double *out, int n);
+
 /* Number of kernels launched by the last forward()/plan run on this thread. */
 unsigned long long simwave_cuda_last_launch_count(void);
 

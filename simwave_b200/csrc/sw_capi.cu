@@ -33,7 +33,9 @@ static double run_forward(const simwave_problem &pb, size_t begin, size_t end)
             plan->run(begin, end);
         plan->download(nullptr, nullptr);
         Timing t = plan->timing;
+        const double t1 = wall();
         plan.reset();
+        t.teardown = wall() - t1;
         t.total = wall() - t0;
         last_timing() = t;
         return t.total;
@@ -85,6 +87,15 @@ void simwave_cuda_last_timing(double *loop, double *h2d, double *d2h, double *to
     if (h2d) *h2d = t.h2d;
     if (d2h) *d2h = t.d2h;
     if (total) *total = t.total;
+}
+
+int simwave_cuda_last_timing_ex(double *out, int n)
+{
+    const sw::Timing &t = sw::last_timing();
+    const double v[6] = {t.loop, t.h2d, t.d2h, t.total, t.run_wall, t.teardown};
+    for (int i = 0; i < n && i < 6; i++)
+        out[i] = v[i];
+    return 6;
 }
 
 unsigned long long simwave_cuda_last_launch_count(void) { return sw::last_timing().launches; }

@@ -26,6 +26,7 @@ struct Options {
 
 struct Timing {
     double loop = 0, h2d = 0, d2h = 0, total = 0;
+    double run_wall = 0, teardown = 0;   // host wall of run(); plan destruction
     unsigned long long launches = 0;
 };
 

@@ -46,9 +46,10 @@ def core():
 
 
 def last_timing():
-    vals = [ctypes.c_double() for _ in range(4)]
-    core().simwave_cuda_last_timing(*[ctypes.byref(v) for v in vals])
-    return dict(zip(("loop", "h2d", "d2h", "total"), [v.value for v in vals]))
+    vals = (ctypes.c_double * 6)()
+    core().simwave_cuda_last_timing_ex(vals, 6)
+    return dict(zip(("loop", "h2d", "d2h", "total", "run_wall", "teardown"),
+                    [float(v) for v in vals]))
 
 
 def cuda_forward(p):

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python tools/parity_report.py > gpurun_out/parity_fast.txt 2>&1; cat gpurun_out/parity_fast.txt
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "exit $?" >> gpurun_out/pytest_gpu.log
-tail -15 gpurun_out/pytest_gpu.log
-SIMWAVE_CUDA_VERBOSE=1 timeout 600 python tools/sweep.py --timesteps 60 --cfgs 0,6,7 --math fast > gpurun_out/sweep_overthrust.txt 2>&1; cat gpurun_out/sweep_overthrust.txt
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; cat gpurun_out/bench_default.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --timesteps 40 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/bench_under_ncu.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:step3d_tiled -s 30 -c 2 -o gpurun_out/prof_tiled_r4_fast -f python bench.py --timesteps 40 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/ncu_full.log

@@ -261,6 +261,12 @@ typedef struct simwave_problem {
     double dt;                /* already rounded to dtype by the caller        */
     size_t space_order;
     size_t num_snapshots;
+    /* Slab decomposition along z (0 = none).  When set, the first / last
+     * space_order/2 planes of every array are GHOST planes owned by the
+     * neighbouring slab (lower z = "up", higher z = "down"); the time loop
+     * refreshes them every step from the neighbour's device over NVLink.
+     * Needs saving_stride == 0 and a connected plan (below). */
+    int slab_up, slab_down;
 } simwave_problem;
 
 simwave_plan *simwave_plan_create(const simwave_problem *problem);
@@ -271,6 +277,26 @@ int simwave_plan_download(simwave_plan *plan, void *u, void *receivers);
  * if that was all zero) so the same plan can be timed repeatedly. */
 int simwave_plan_reset(simwave_plan *plan);
 void simwave_plan_destroy(simwave_plan *plan);
+
+/*
+ * Slab decomposition (one process per GPU).  Each process creates a plan for
+ * its z-slab (ghost planes included, slab_up / slab_down set), exports an
+ * opaque descriptor of its wavefield buffers (CUDA IPC handles), exchanges
+ * descriptors with its neighbours by any host channel (torch.distributed,
+ * MPI, files ...) and connects.  From then on simwave_plan_run() keeps the
+ * ghost planes current: after every step the slab's outermost owned planes are
+ * written into the neighbours' ghost planes through the peer mapping and a
+ * per-step flag is published in the neighbour's memory; the next step waits on
+ * the flags on the device.  No host synchronisation inside the time loop.
+ * All slabs must call simwave_plan_run() with the same timestep range, and a
+ * host barrier must separate simwave_plan_reset() / connect from the next run.
+ */
+#define SIMWAVE_SLAB_DESC_BYTES 512
+int simwave_plan_slab_export(simwave_plan *plan, void *desc /* SIMWAVE_SLAB_DESC_BYTES */);
+/* `up_desc` / `down_desc`: descriptors exported by the neighbouring processes
+ * (NULL where the problem has no such neighbour). */
+int simwave_plan_slab_connect(simwave_plan *plan, const void *up_desc,
+                              const void *down_desc);
 
 #ifdef __cplusplus
 }

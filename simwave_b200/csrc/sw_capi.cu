@@ -159,6 +159,32 @@ int simwave_plan_reset(simwave_plan *plan)
     }
 }
 
+int simwave_plan_slab_export(simwave_plan *plan, void *desc)
+{
+    try {
+        if (!plan || !desc)
+            throw sw::Error("null plan or descriptor");
+        plan->impl->slab_export(desc);
+        return 0;
+    } catch (const std::exception &e) {
+        sw::set_last_error(e.what());
+        return -1;
+    }
+}
+
+int simwave_plan_slab_connect(simwave_plan *plan, const void *up_desc, const void *down_desc)
+{
+    try {
+        if (!plan)
+            throw sw::Error("null plan");
+        plan->impl->slab_connect(up_desc, down_desc);
+        return 0;
+    } catch (const std::exception &e) {
+        sw::set_last_error(e.what());
+        return -1;
+    }
+}
+
 void simwave_plan_destroy(simwave_plan *plan) { delete plan; }
 
 // ---- the eight drop-in entry points -----------------------------------------

@@ -248,6 +248,71 @@ static const TiledLaunchFn kTiledLaunch[kMaxRadius + 1] = {
     tiled3d_launch_r9, tiled3d_launch_r10};
 
 // ---------------------------------------------------------------------------
+// slab decomposition plumbing
+// ---------------------------------------------------------------------------
+struct SlabDesc {
+    unsigned magic;
+    int dtypeBytes, nS, nM, nF, r, lpad, device;
+    long long pitch, planeStride;
+    unsigned long long slotOffset[3];   // field base (element (0,0,0)) from the mapped base
+    unsigned long long flagsOffset;
+    cudaIpcMemHandle_t slot[3];
+    cudaIpcMemHandle_t flags;
+};
+static_assert(sizeof(SlabDesc) <= SIMWAVE_SLAB_DESC_BYTES, "descriptor too large");
+constexpr unsigned kSlabMagic = 0x534c4142u;   // "SLAB"
+
+// flags[0]: last step whose halo the UP neighbour has delivered, [1]: same for
+// DOWN, [2]: error word (1 = timed out)
+__global__ void slab_wait_kernel(int *flags, int needUp, int needDown, int value)
+{
+    const long long start = clock64();
+    for (int side = 0; side < 2; side++) {
+        if (!(side == 0 ? needUp : needDown))
+            continue;
+        for (;;) {
+            int v;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + side)
+                         : "memory");
+            if (v >= value)
+                break;
+            if (clock64() - start > 40000000000LL) {   // ~20 s: neighbour is gone
+                flags[2] = 1;
+                return;
+            }
+            __nanosleep(200);
+        }
+    }
+}
+
+__global__ void slab_publish_kernel(int *peerFlag, int value)
+{
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peerFlag), "r"(value) : "memory");
+}
+
+// handle + offset of a device pointer inside its cudaMalloc allocation
+static void ipc_export(const void *ptr, cudaIpcMemHandle_t *handle, unsigned long long *offset)
+{
+    typedef CUresult (*RangeFn)(CUdeviceptr *, size_t *, CUdeviceptr);
+    static RangeFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        SW_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p)
+            throw Error("driver does not provide cuMemGetAddressRange");
+        fn = (RangeFn)p;
+    }
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (fn(&base, &size, (CUdeviceptr)ptr) != CUDA_SUCCESS)
+        throw Error("cuMemGetAddressRange failed");
+    SW_CUDA(cudaIpcGetMemHandle(handle, (void *)base));
+    *offset = (unsigned long long)((CUdeviceptr)ptr - base);
+}
+
+// ---------------------------------------------------------------------------
 // Plan
 // ---------------------------------------------------------------------------
 template <typename T>
@@ -258,6 +323,8 @@ public:
     void run(size_t begin, size_t end) override;
     void download(void *u, void *receivers) override;
     void reset() override;
+    void slab_export(void *desc) override;
+    void slab_connect(const void *up, const void *down) override;
 
 private:
     using StepFn = void (*)(int, const StepArgs<T> &, cudaStream_t);
@@ -323,6 +390,17 @@ private:
     size_t recBegin_ = 0, recEnd_ = 0;   // receiver rows produced so far [begin,end)
 
     std::unique_ptr<HostDrain> drain_;
+
+    // slab decomposition: neighbours' slot buffers and flag words, mapped
+    // through CUDA IPC; flags_ = {from up, from down, error}
+    bool slabUp_ = false, slabDown_ = false, slabConnected_ = false;
+    DeviceBuffer slabFlags_;
+    T *peerSlot_[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    int *peerFlags_[2] = {nullptr, nullptr};
+    int peerNS_[2] = {0, 0};
+    std::vector<void *> ipcMapped_;
+    void slab_wait(size_t n);
+    void slab_push(size_t n, size_t slot);
 };
 
 template <typename T>
@@ -383,6 +461,10 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     nrec_ = pb.num_receivers;
     if (numSlots_ < 3)
         throw Error("u must hold at least 3 slots");
+    slabUp_ = pb.slab_up != 0;
+    slabDown_ = pb.slab_down != 0;
+    if ((slabUp_ || slabDown_) && (ndim_ != 3 || stride_ != 0))
+        throw Error("slab decomposition needs a 3D problem with saving_stride == 0");
 
     SW_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     SW_CUDA(cudaEventCreate(&evBegin_));
@@ -531,6 +613,13 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     }
 
     drain_.reset(new HostDrain(device_, 32u << 20));
+    if (slabUp_ || slabDown_) {
+        // the three slots stay resident so that the neighbours can map them
+        for (size_t s = 0; s < 3; s++)
+            ensure_live(s);
+        slabFlags_.alloc(4 * sizeof(int));
+        SW_CUDA(cudaMemsetAsync(slabFlags_.get(), 0, slabFlags_.bytes(), stream_));
+    }
     SW_CUDA(cudaStreamSynchronize(stream_));
     timing.h2d = wall() - t0;
 }
@@ -543,6 +632,8 @@ Plan<T>::~Plan()
         cudaStreamSynchronize(stream_);
         cudaStreamDestroy(stream_);
     }
+    for (void *p : ipcMapped_)
+        cudaIpcCloseMemHandle(p);
     if (evBegin_) cudaEventDestroy(evBegin_);
     if (evEnd_) cudaEventDestroy(evEnd_);
 }
@@ -824,6 +915,8 @@ void Plan<T>::run(size_t begin, size_t end)
 {
     if (begin < 1 || end > waveletSize_)
         throw Error("timestep range outside [1, wavelet_size]");
+    if ((slabUp_ || slabDown_) && !slabConnected_)
+        throw Error("slab plan is not connected to its neighbours");
     const double t0 = wall();
     SW_CUDA(cudaEventRecord(evBegin_, stream_));
     if (recBegin_ == recEnd_) { recBegin_ = begin - 1; recEnd_ = begin - 1; }
@@ -846,12 +939,16 @@ void Plan<T>::run(size_t begin, size_t end)
         a.cur = live_[curT_];
         a.next = live_[nextT_];
 
+        if (slabUp_ || slabDown_)
+            slab_wait(n);
         launch_receivers(a.cur, n);
         launch_step(a);
         launch_sources(a, n);
         if (!a.fuse_bc)
             launch_boundaries(a.next);
         dirty_[nextT_] = true;
+        if (slabUp_ || slabDown_)
+            slab_push(n, nextT_);
 
         // slot bookkeeping for saving_stride > 1, as 3d/wave.c:569-618
         if (stride_ > 1) {
@@ -878,6 +975,12 @@ void Plan<T>::run(size_t begin, size_t end)
     recEnd_ = std::max(recEnd_, end);
     SW_CUDA(cudaEventRecord(evEnd_, stream_));
     SW_CUDA(cudaEventSynchronize(evEnd_));
+    if (slabUp_ || slabDown_) {
+        int flags[4] = {0, 0, 0, 0};
+        SW_CUDA(cudaMemcpy(flags, slabFlags_.get(), sizeof(flags), cudaMemcpyDeviceToHost));
+        if (flags[2])
+            throw Error("slab halo exchange timed out waiting for a neighbour");
+    }
     float ms = 0;
     SW_CUDA(cudaEventElapsedTime(&ms, evBegin_, evEnd_));
     timing.loop = ms * 1e-3;
@@ -913,14 +1016,108 @@ void Plan<T>::reset()
 {
     drain_->wait_idle();
     SW_CUDA(cudaStreamSynchronize(stream_));
-    for (auto &kv : live_)
-        give_back(kv.second);
-    live_.clear();
-    dirty_.clear();
+    const bool slab = slabUp_ || slabDown_;
+    if (slab) {
+        // the neighbours hold mappings of these buffers: refill them in place
+        for (size_t s = 0; s < 3; s++) {
+            T *buf = live_.at(s);
+            SW_CUDA(cudaMemsetAsync((char *)(buf - g_.lpad - guard_), 0, fieldBytes_, stream_));
+            if (!slotZero_[s])
+                upload_dense(hostU_ + s * denseCells_, buf);
+            dirty_[s] = false;
+        }
+        SW_CUDA(cudaMemsetAsync(slabFlags_.get(), 0, slabFlags_.bytes(), stream_));
+    } else {
+        for (auto &kv : live_)
+            give_back(kv.second);
+        live_.clear();
+        dirty_.clear();
+    }
     prevT_ = 0; curT_ = 1; nextT_ = 2;
     recBegin_ = recEnd_ = 0;
     SW_CUDA(cudaMemsetAsync(recOut_.get(), 0, recOut_.bytes(), stream_));
     timing.launches = 0;
+    SW_CUDA(cudaStreamSynchronize(stream_));
+}
+
+template <typename T>
+void Plan<T>::slab_export(void *out)
+{
+    if (!(slabUp_ || slabDown_))
+        throw Error("not a slab plan");
+    SlabDesc d;
+    std::memset(&d, 0, sizeof(d));
+    d.magic = kSlabMagic;
+    d.dtypeBytes = (int)sizeof(T);
+    d.nS = g_.nS; d.nM = g_.nM; d.nF = g_.nF; d.r = g_.r; d.lpad = g_.lpad;
+    d.device = device_;
+    d.pitch = g_.pitch; d.planeStride = g_.planeStride;
+    for (size_t s = 0; s < 3; s++)
+        ipc_export(live_.at(s), &d.slot[s], &d.slotOffset[s]);
+    ipc_export(slabFlags_.get(), &d.flags, &d.flagsOffset);
+    std::memset(out, 0, SIMWAVE_SLAB_DESC_BYTES);
+    std::memcpy(out, &d, sizeof(d));
+}
+
+template <typename T>
+void Plan<T>::slab_connect(const void *up, const void *down)
+{
+    if ((slabUp_ && !up) || (slabDown_ && !down))
+        throw Error("slab_connect: missing neighbour descriptor");
+    const void *descs[2] = {slabUp_ ? up : nullptr, slabDown_ ? down : nullptr};
+    for (int side = 0; side < 2; side++) {
+        if (!descs[side])
+            continue;
+        SlabDesc d;
+        std::memcpy(&d, descs[side], sizeof(d));
+        if (d.magic != kSlabMagic || d.dtypeBytes != (int)sizeof(T) || d.nM != g_.nM ||
+            d.nF != g_.nF || d.r != g_.r || d.pitch != g_.pitch || d.lpad != g_.lpad)
+            throw Error("slab_connect: neighbour slab has a different plane layout");
+        auto open = [&](const cudaIpcMemHandle_t &h) {
+            void *p = nullptr;
+            SW_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            ipcMapped_.push_back(p);
+            return (char *)p;
+        };
+        for (int s = 0; s < 3; s++)
+            peerSlot_[side][s] = (T *)(open(d.slot[s]) + d.slotOffset[s]);
+        // my up neighbour records my deliveries in ITS "from down" word and vice versa
+        peerFlags_[side] = (int *)(open(d.flags) + d.flagsOffset) + (side == 0 ? 1 : 0);
+        peerNS_[side] = d.nS;
+    }
+    slabConnected_ = true;
+}
+
+// before step n reads the ghost planes of u_cur: the neighbours must have
+// delivered the halo they produced in step n-1
+template <typename T>
+void Plan<T>::slab_wait(size_t n)
+{
+    slab_wait_kernel<<<1, 1, 0, stream_>>>(slabFlags_.as<int>(), slabUp_ ? 1 : 0,
+                                           slabDown_ ? 1 : 0, (int)n - 1);
+    check_launch("slab_wait_kernel");
+}
+
+// after step n: my outermost owned planes of u_next become the neighbours'
+// ghost planes (whole padded planes, so F/M halo cells travel too), then the
+// per-step flag is published in the neighbour's memory
+template <typename T>
+void Plan<T>::slab_push(size_t n, size_t slot)
+{
+    const int r = g_.r;
+    const size_t planeBytes = (size_t)g_.planeStride * sizeof(T);
+    const T *mine = live_.at(slot);
+    for (int side = 0; side < 2; side++) {
+        if (!(side == 0 ? slabUp_ : slabDown_))
+            continue;
+        const long long srcPlane = (side == 0) ? r : g_.nS - 2 * r;
+        const long long dstPlane = (side == 0) ? peerNS_[side] - r : 0;
+        SW_CUDA(cudaMemcpyAsync(peerSlot_[side][slot] + dstPlane * g_.planeStride - g_.lpad,
+                                mine + srcPlane * g_.planeStride - g_.lpad, r * planeBytes,
+                                cudaMemcpyDefault, stream_));
+        slab_publish_kernel<<<1, 1, 0, stream_>>>(peerFlags_[side], (int)n);
+        check_launch("slab_publish_kernel");
+    }
 }
 
 std::unique_ptr<PlanBase> make_plan(const simwave_problem &pb, const Options &opt)

@@ -96,6 +96,8 @@ public:
     virtual void run(size_t begin, size_t end) = 0;
     virtual void download(void *u, void *receivers) = 0;
     virtual void reset() = 0;
+    virtual void slab_export(void *desc) = 0;
+    virtual void slab_connect(const void *up, const void *down) = 0;
     Timing timing;
 };
 

@@ -61,6 +61,12 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true",
                     help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-slab", action="store_true",
+                    help="skip the slab-decomposition leg")
+    ap.add_argument("--slab-planes", type=int, default=128,
+                    help="owned z-planes per GPU in the slab leg")
+    ap.add_argument("--slab-n", type=int, default=1040)
+    ap.add_argument("--slab-timesteps", type=int, default=60)
     return ap.parse_args()
 
 
@@ -216,75 +222,6 @@ def workload_config(args, p, timesteps):
 
 
 # ---------------------------------------------------------------------------
-def make_problem_struct(p, keep):
-    """simwave_problem (include/simwave_cuda.h) for the plan API."""
-    class Problem(ctypes.Structure):
-        _fields_ = [
-            ("ndim", ctypes.c_int), ("dtype_bytes", ctypes.c_int),
-            ("u", ctypes.c_void_p), ("velocity", ctypes.c_void_p),
-            ("density", ctypes.c_void_p), ("damp", ctypes.c_void_p),
-            ("wavelet", ctypes.c_void_p), ("wavelet_size", ctypes.c_size_t),
-            ("wavelet_count", ctypes.c_size_t),
-            ("coeff_order2", ctypes.c_void_p), ("coeff_order1", ctypes.c_void_p),
-            ("boundary_conditions", ctypes.c_void_p),
-            ("src_points_interval", ctypes.c_void_p),
-            ("src_points_values", ctypes.c_void_p),
-            ("src_points_values_size", ctypes.c_size_t),
-            ("src_points_values_offset", ctypes.c_void_p),
-            ("rec_points_interval", ctypes.c_void_p),
-            ("rec_points_values", ctypes.c_void_p),
-            ("rec_points_values_size", ctypes.c_size_t),
-            ("rec_points_values_offset", ctypes.c_void_p),
-            ("receivers", ctypes.c_void_p),
-            ("num_sources", ctypes.c_size_t), ("num_receivers", ctypes.c_size_t),
-            ("nz", ctypes.c_size_t), ("nx", ctypes.c_size_t), ("ny", ctypes.c_size_t),
-            ("dz", ctypes.c_double), ("dx", ctypes.c_double), ("dy", ctypes.c_double),
-            ("saving_stride", ctypes.c_size_t), ("dt", ctypes.c_double),
-            ("space_order", ctypes.c_size_t), ("num_snapshots", ctypes.c_size_t),
-        ]
-
-    def ptr(a):
-        if a is None:
-            return None
-        keep.append(a)
-        return a.ctypes.data
-
-    shape = p["velocity"].shape
-    ndim = len(shape)
-    f = p["velocity"].dtype.type
-    h = [float(f(x)) for x in p["spacing"]]
-    pb = Problem()
-    pb.ndim = ndim
-    pb.dtype_bytes = p["velocity"].dtype.itemsize
-    pb.u = ptr(p["u"]); pb.velocity = ptr(p["velocity"])
-    pb.density = ptr(p.get("density")); pb.damp = ptr(p["damp"])
-    pb.wavelet = ptr(p["wavelet"]); pb.wavelet_size = p["wavelet"].shape[0]
-    pb.wavelet_count = 1 if p["wavelet"].ndim == 1 else p["wavelet"].shape[1]
-    pb.coeff_order2 = ptr(p["coeff2"])
-    pb.coeff_order1 = ptr(p["coeff1"]) if p.get("density") is not None else None
-    pb.boundary_conditions = ptr(p["bc"])
-    pb.src_points_interval = ptr(p["src_intervals"])
-    pb.src_points_values = ptr(p["src_values"])
-    pb.src_points_values_size = len(p["src_values"])
-    pb.src_points_values_offset = ptr(p["src_offsets"])
-    pb.rec_points_interval = ptr(p["rec_intervals"])
-    pb.rec_points_values = ptr(p["rec_values"])
-    pb.rec_points_values_size = len(p["rec_values"])
-    pb.rec_points_values_offset = ptr(p["rec_offsets"])
-    pb.receivers = ptr(p["receivers"])
-    pb.num_sources = len(p["src_offsets"]) - 1
-    pb.num_receivers = len(p["rec_offsets"]) - 1
-    pb.nz, pb.nx = shape[0], shape[1]
-    pb.ny = shape[2] if ndim == 3 else 0
-    pb.dz, pb.dx = h[0], h[1]
-    pb.dy = h[2] if ndim == 3 else 0.0
-    pb.saving_stride = p["saving_stride"]
-    pb.dt = float(f(p["dt"]))
-    pb.space_order = p["space_order"]
-    pb.num_snapshots = p["u"].shape[0]
-    return pb
-
-
 def pinned_like(a):
     """Copy of ndarray `a` in page-locked host memory (torch allocator)."""
     import torch
@@ -299,6 +236,59 @@ def pinned_like(a):
 out_keepalive = []
 
 
+def run_slab_leg(args, rank, world, dist, barrier, max_over_ranks):
+    """One large 3D model split into z-slabs, one per GPU, ghost planes kept
+    current on the device over NVLink (simwave_b200/slab.py).  Weak scaling:
+    --slab-planes owned planes per GPU.  Returns the "slab" object of the
+    bench line (None on ranks other than 0)."""
+    import workloads
+    from simwave_b200 import slab
+    q = workloads.slab_3d(rank=rank, world=world,
+                          planes_per_gpu=args.slab_planes, n=args.slab_n,
+                          timesteps=args.slab_timesteps)
+    r = q["space_order"] // 2
+    T = q["end_timestep"]
+    plan = slab.Plan(q)
+    if world > 1:
+        def gather_bytes(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        slab.connect_neighbours(plan, rank, world, gather_bytes)
+    times = []
+    for i in range(1 + max(1, args.steps)):
+        plan.reset()
+        barrier()
+        t = plan.run(1, T)
+        if i >= 1:
+            times.append(t)
+    total = max_over_ranks(sum(times))
+    plan.destroy()
+    nx, ny = q["velocity"].shape[1:]
+    pts = q["owned_planes"] * (nx - 2 * r) * (ny - 2 * r)
+    bpp = workloads.bytes_per_point(q)
+    halo = (int(q["slab_up"]) + int(q["slab_down"])) * r * nx * ny * 4
+    if rank != 0:
+        return None
+    peak, _ = measured_peak()
+    value = world * pts * T * len(times) / total / 1e9
+    return {
+        "value": value, "unit": "Gpts/s", "scaling": "weak",
+        "ms_per_timestep": 1e3 * total / len(times) / T,
+        "roofline_frac_per_gpu": value / world * bpp / peak,
+        "config": {
+            "workload": "slab_3d (C4-shaped): global grid %s (extended), "
+                        "variable density, space_order %d, %d owned planes per "
+                        "GPU, %d time steps" % (
+                            "x".join(map(str, q["global_shape"])),
+                            q["space_order"], q["owned_planes"], T),
+            "exchange": "per time step, r=%d planes per face pushed into the "
+                        "neighbour's ghost planes through CUDA IPC peer "
+                        "mappings (NVLink), device-side step flags" % r,
+            "halo_bytes_per_step_per_gpu": halo},
+    }
+
+
 def run_ours(args, p, rank, world, local_rank):
     import torch
     import workloads
@@ -311,18 +301,11 @@ def run_ours(args, p, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    from simwave_b200 import slab
     lib = core()
     if lib.simwave_cuda_device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device; the CUDA backend has no "
                          "CPU fallback")
-    lib.simwave_plan_create.restype = ctypes.c_void_p
-    lib.simwave_plan_run.argtypes = [ctypes.c_void_p, ctypes.c_size_t,
-                                     ctypes.c_size_t,
-                                     ctypes.POINTER(ctypes.c_double)]
-    lib.simwave_plan_reset.argtypes = [ctypes.c_void_p]
-    lib.simwave_plan_download.argtypes = [ctypes.c_void_p, ctypes.c_void_p,
-                                          ctypes.c_void_p]
-    lib.simwave_plan_destroy.argtypes = [ctypes.c_void_p]
 
     T = p["end_timestep"]
     pts = workloads.interior_points(p)
@@ -342,20 +325,11 @@ def run_ours(args, p, rank, world, local_rank):
         return float(t.item())
 
     # ---- device-resident throughput (plan API) -----------------------------
-    keep = []
-    pb = make_problem_struct(p, keep)
-    plan = lib.simwave_plan_create(ctypes.byref(pb))
-    if not plan:
-        raise SystemExit("plan_create failed: " +
-                         lib.simwave_cuda_last_error().decode())
-    loop = ctypes.c_double()
+    plan = slab.Plan(p)
 
     def one_step():
-        if lib.simwave_plan_reset(plan) != 0 or \
-                lib.simwave_plan_run(plan, 1, T, ctypes.byref(loop)) != 0:
-            raise SystemExit("plan_run failed: " +
-                             lib.simwave_cuda_last_error().decode())
-        return loop.value
+        plan.reset()
+        return plan.run(1, T)
 
     for _ in range(args.warmup):
         one_step()
@@ -365,10 +339,10 @@ def run_ours(args, p, rank, world, local_rank):
         device_seconds = [one_step() for _ in range(args.steps)]
         barrier()
         wall = time.perf_counter() - wall0
-    launches = lib.simwave_cuda_last_launch_count() * args.steps
+    launches = plan.launches() * args.steps
     dev_total = max_over_ranks(sum(device_seconds))
     wall = max_over_ranks(wall)
-    lib.simwave_plan_destroy(plan)
+    plan.destroy()
 
     value = world * pts * T * args.steps / dev_total / 1e9
     achieved = pts * T * args.steps * bpp / dev_total / 1e9   # per GPU
@@ -428,6 +402,12 @@ def run_ours(args, p, rank, world, local_rank):
             cpu = {"value": None, "unit": "Gpts/s", "cores": host_threads(),
                    "kind": "port", "sample": "failed: %s" % e}
 
+    # ---- slab decomposition leg (C4-shaped, weak scaling) --------------------
+    slab_result = None
+    if not args.no_slab:
+        slab_result = run_slab_leg(args, rank, world, dist, barrier,
+                                   max_over_ranks)
+
     if rank == 0:
         line = {
             "metric": "Gpts/s", "value": value, "unit": "Gpts/s",
@@ -447,6 +427,7 @@ def run_ours(args, p, rank, world, local_rank):
                         "the loop (source and receiver kernels included)" % bpp},
             "cpu_baseline": cpu,
             "e2e": e2e,
+            "slab": slab_result,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "wall_ms_per_step": 1e3 * wall / args.steps,

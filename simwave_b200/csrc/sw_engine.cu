@@ -235,8 +235,8 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-typedef bool (*TiledQueryFn)(int, TiledInfo *);
-typedef bool (*TiledLaunchFn)(int, int, const StepArgs<float> &, const StepMaps &,
+typedef bool (*TiledQueryFn)(int, bool, TiledInfo *);
+typedef bool (*TiledLaunchFn)(int, bool, int, const StepArgs<float> &, const StepMaps &,
                               const unsigned char *, int, cudaStream_t);
 static const TiledQueryFn kTiledQuery[kMaxRadius + 1] = {
     nullptr, tiled3d_query_r1, tiled3d_query_r2, tiled3d_query_r3, tiled3d_query_r4,
@@ -374,6 +374,7 @@ private:
     const CUtensorMap &field_map(const T *base, bool halo);
     void choose_tiling();
     DeviceBuffer qflags_;   // [nS][tilesM][tilesF]: damping profile non-zero in the tile?
+    DeviceBuffer frF_, frM_, frS_;   // first derivatives of the density (tiled variable density)
 
     cudaStream_t stream_ = nullptr;
     cudaEvent_t evBegin_ = nullptr, evEnd_ = nullptr;
@@ -742,18 +743,18 @@ void Plan<T>::choose_tiling()
 {
     useTiled_ = false;
     if constexpr (std::is_same<T, float>::value) {
-        if (opt_.simple || ndim_ != 3 || varden_)
+        if (opt_.simple || ndim_ != 3 || (varden_ && args_.quirk))
             return;
         const int r = g_.r;
         // default configuration, overridable as SIMWAVE_CUDA_TILE=<cfg>[:<zchunk>]
-        int cfg = (r <= 5) ? 6 : 0;
+        int cfg = (r <= 5 && !varden_) ? 6 : 0;
         int zchunk = 0;
         if (const char *e = std::getenv("SIMWAVE_CUDA_TILE")) {
             cfg = std::atoi(e);
             if (const char *c = std::strchr(e, ':'))
                 zchunk = std::atoi(c + 1);
         }
-        if (!kTiledQuery[r](cfg, &tiledInfo_))
+        if (!kTiledQuery[r](cfg, varden_, &tiledInfo_))
             throw Error("SIMWAVE_CUDA_TILE: no such tile configuration");
         int maxSmem = 0;
         SW_CUDA(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
@@ -787,7 +788,8 @@ void Plan<T>::choose_tiling()
                 const int real = (interior + len - 1) / len;
                 const double waves = tilesF * tilesM * real / slots;
                 const double fill = waves / std::ceil(waves);
-                const double traffic = 20.0 / (20.0 + 2.0 * r * haloBytes / len);
+                const double alg = varden_ ? 36.0 : 20.0;
+                const double traffic = alg / (alg + 2.0 * r * haloBytes / len);
                 const double score = fill * traffic;
                 if (score > best + 1e-9) { best = score; bestChunks = chunks; }
             }
@@ -804,6 +806,19 @@ void Plan<T>::choose_tiling()
                                                 tiledInfo_.tileF(),
                                                 qflags_.as<unsigned char>());
         check_launch("qflag_kernel");
+        if (varden_) {
+            new_field(frF_);
+            new_field(frM_);
+            new_field(frS_);
+            dim3 gg((g_.nF - 2 * r + 127) / 128, g_.nM - 2 * r, interior);
+            if (opt_.math == MATH_STRICT)
+                rho_gradient_kernel<float, MATH_STRICT><<<gg, 128, 0, stream_>>>(
+                    args_, field_base(frF_), field_base(frM_), field_base(frS_));
+            else
+                rho_gradient_kernel<float, MATH_FAST><<<gg, 128, 0, stream_>>>(
+                    args_, field_base(frF_), field_base(frM_), field_base(frS_));
+            check_launch("rho_gradient_kernel");
+        }
         if (std::getenv("SIMWAVE_CUDA_VERBOSE"))
             std::fprintf(stderr,
                          "simwave_b200: tiled 3D kernel cfg %d, tile %dx%d, z chunk %d (%d chunks), "
@@ -851,8 +866,14 @@ void Plan<T>::launch_step(const StepArgs<T> &a)
             maps.prev = field_map(a.prev, false);
             maps.c0 = field_map(a.c0, false);
             maps.q = field_map(a.q, false);
-            if (!kTiledLaunch[g_.r](tiledCfg_, opt_.math, a, maps, qflags_.as<unsigned char>(),
-                                    zChunk_, stream_))
+            if (varden_) {
+                maps.rho = field_map(a.rho, false);
+                maps.frF = field_map(field_base(frF_), false);
+                maps.frM = field_map(field_base(frM_), false);
+                maps.frS = field_map(field_base(frS_), false);
+            }
+            if (!kTiledLaunch[g_.r](tiledCfg_, varden_, opt_.math, a, maps,
+                                    qflags_.as<unsigned char>(), zChunk_, stream_))
                 throw Error("tiled kernel configuration vanished");
             check_launch("tiled step kernel");
             return;

@@ -28,10 +28,11 @@ namespace sw {
 // tensor maps of one time step: u_cur with halo; u_prev, c0, q halo-free
 struct StepMaps {
     CUtensorMap cur, prev, c0, q;
+    CUtensorMap rho, frF, frM, frS;     // variable density only
 };
 #define SW_DECL_TILED(R)                                                              \
-    bool tiled3d_query_r##R(int cfg, TiledInfo *info);                                \
-    bool tiled3d_launch_r##R(int cfg, int math, const StepArgs<float> &a,             \
+    bool tiled3d_query_r##R(int cfg, bool varden, TiledInfo *info);                   \
+    bool tiled3d_launch_r##R(int cfg, bool varden, int math, const StepArgs<float> &a, \
                              const StepMaps &maps, const unsigned char *qflags,       \
                              int zChunk, cudaStream_t stream);
 SW_DECL_TILED(1) SW_DECL_TILED(2) SW_DECL_TILED(3) SW_DECL_TILED(4) SW_DECL_TILED(5)

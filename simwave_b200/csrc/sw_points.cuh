@@ -36,6 +36,35 @@ __global__ void model_kernel(Grid g, const T *__restrict__ velocity, const T *__
         }
 }
 
+// First derivatives of the density along every axis at the interior points,
+// accumulated ring by ring exactly as the step kernels do
+// (variable_density/3d/wave.c:180-194).  They are constant in time; the tiled
+// kernel streams them instead of keeping a halo of the density.
+template <typename T, int MATH>
+__global__ void rho_gradient_kernel(const __grid_constant__ StepArgs<T> a, T *__restrict__ frF,
+                                    T *__restrict__ frM, T *__restrict__ frS)
+{
+    const Grid &g = a.g;
+    const int r = g.r;
+    const int f = r + blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = r + blockIdx.y;
+    const int s = r + blockIdx.z;
+    if (f >= g.nF - r)
+        return;
+    const long long p = g.at(s, m, f);
+    const T *d = a.rho + p;
+    T gF = T(0), gM = T(0), gS = T(0);
+    for (int ir = 1; ir <= r; ir++) {
+        const long long oM = (long long)ir * g.pitch, oS = (long long)ir * g.planeStride;
+        gF = ring_diff<T, MATH>(gF, a.c1[ir], d[ir], d[-ir]);
+        gM = ring_diff<T, MATH>(gM, a.c1[ir], d[oM], d[-oM]);
+        gS = ring_diff<T, MATH>(gS, a.c1[ir], d[oS], d[-oS]);
+    }
+    frF[p] = gF;
+    frM[p] = gM;
+    frS[p] = gS;
+}
+
 // flags[(s*tilesM + tm)*tilesF + tf] = 1 where q != 0 somewhere among the
 // interior points of tile (tm,tf) on plane s.  One block per (tile, plane);
 // blockIdx.z counts interior planes.

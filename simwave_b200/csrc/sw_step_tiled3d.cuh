@@ -1,4 +1,4 @@
-// Tiled 3D step kernel for sm_100a (float32, constant density).
+// Tiled 3D step kernel for sm_100a (float32; constant and variable density).
 //
 // Decomposition: a CTA owns a (BX x BY) tile of the (M,F) = (x,y) plane and
 // marches along S (= z) over a chunk of planes.  The CTA is warp-specialised:
@@ -22,6 +22,13 @@
 //     128-bit global stores; the damping factors and the boundary conditions
 //     are applied in the same kernel (store_with_boundaries semantics), with
 //     a branch-free store for tiles and planes that touch no boundary.
+//
+// Variable density: the density enters the update only through its first
+// derivatives, which do not change in time.  They are computed once per run
+// (rho_gradient_kernel, same ring order and rounding as the plain kernel) and
+// streamed as three more halo-free tiles next to rho itself, so the kernel
+// needs neither a halo nor a register queue for the density; the first
+// derivatives of u reuse the neighbours already loaded for the Laplacian.
 //
 // The arithmetic goes through the same helpers as the plain kernel, in the
 // same order, so the two kernels agree bit for bit in either math mode (and
@@ -85,8 +92,9 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 }
 
 // ---- tile geometry -------------------------------------------------------------
-template <int R, int PM, int TX, int TY, int PF, int PS>
+template <int R, int PM, int TX, int TY, int PF, int PS, bool VARDEN = false>
 struct Tile3D {
+    static constexpr int NSTR = VARDEN ? 7 : 3;      // prev | c0 | q [| rho | frF | frM | frS]
     static constexpr int RP = (R + 3) / 4 * 4;       // F halo rounded to a float4
     static constexpr int BX = TY * PM;               // rows (M) per tile
     static constexpr int BY = TX * 4;                // columns (F) per tile
@@ -99,9 +107,9 @@ struct Tile3D {
     static constexpr int SLOT_FLOATS = SLOT_BYTES / 4;
     static constexpr int STR_BYTES = BX * BY * 4;    // one stream tile (multiple of 128)
     static constexpr int STR_FLOATS = BX * BY;
-    static constexpr int STAGE_FLOATS = 3 * STR_FLOATS;   // prev | c0 | q
+    static constexpr int STAGE_FLOATS = NSTR * STR_FLOATS;
     static constexpr int RING_BYTES = NS * SLOT_BYTES;
-    static constexpr int STREAM_BYTES = NT * 3 * STR_BYTES;
+    static constexpr int STREAM_BYTES = NT * NSTR * STR_BYTES;
     static constexpr int NBARS = 2 * NS + 2 * NT;
     static constexpr int SMEM_BYTES = RING_BYTES + STREAM_BYTES + NBARS * 8 + NT * 4;
     static constexpr int CONSUMERS = TX * TY;
@@ -192,13 +200,13 @@ __device__ __forceinline__ void store_row4(const StepArgs<float> &a, int s, int 
     }
 }
 
-template <int R, int PM, int TX, int TY, int PF, int PS, int MATH, int MINB>
+template <int R, int PM, int TX, int TY, int PF, int PS, int MATH, int MINB, bool VARDEN>
 __global__ void __launch_bounds__(TX *TY + 32, MINB)
 step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                     const __grid_constant__ StepMaps maps,
                     const unsigned char *__restrict__ qflags, int zChunk)
 {
-    using TL = Tile3D<R, PM, TX, TY, PF, PS>;
+    using TL = Tile3D<R, PM, TX, TY, PF, PS, VARDEN>;
     constexpr int RP = TL::RP, BYH = TL::BYH, NS = TL::NS, NT = TL::NT;
     constexpr int Q = 2 * R + 1;
     constexpr int NCW = TL::CONSUMERS / 32;
@@ -256,9 +264,19 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 mbar_wait(&emptyStr[st], ((j / NT) - 1) & 1);
             float *dst = streams + st * TL::STAGE_FLOATS;
             stageHasQ[st] = hasQ;
-            mbar_expect_tx(&fullStr[st], (hasQ ? 3 : 2) * TL::STR_BYTES);
+            mbar_expect_tx(&fullStr[st], ((hasQ ? 3 : 2) + (VARDEN ? 4 : 0)) * TL::STR_BYTES);
             tma_load_3d(dst, &maps.prev, &fullStr[st], g.lpad + f0, m0, z0 + j);
             tma_load_3d(dst + TL::STR_FLOATS, &maps.c0, &fullStr[st], g.lpad + f0, m0, z0 + j);
+            if (VARDEN) {
+                tma_load_3d(dst + 3 * TL::STR_FLOATS, &maps.rho, &fullStr[st], g.lpad + f0, m0,
+                            z0 + j);
+                tma_load_3d(dst + 4 * TL::STR_FLOATS, &maps.frF, &fullStr[st], g.lpad + f0, m0,
+                            z0 + j);
+                tma_load_3d(dst + 5 * TL::STR_FLOATS, &maps.frM, &fullStr[st], g.lpad + f0, m0,
+                            z0 + j);
+                tma_load_3d(dst + 6 * TL::STR_FLOATS, &maps.frS, &fullStr[st], g.lpad + f0, m0,
+                            z0 + j);
+            }
             if (hasQ)
                 tma_load_3d(dst + 2 * TL::STR_FLOATS, &maps.q, &fullStr[st], g.lpad + f0, m0,
                             z0 + j);
@@ -378,9 +396,12 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 w[4 * b + 0] = v.x; w[4 * b + 1] = v.y; w[4 * b + 2] = v.z; w[4 * b + 3] = v.w;
             }
             Stencil3<float, MATH> acc[4];
+            float fpF[4], fpM[4], fpS[4];       // first derivatives of u (variable density)
 #pragma unroll
-            for (int c = 0; c < 4; c++)
+            for (int c = 0; c < 4; c++) {
                 acc[c].begin(a, qv[i][c][R]);
+                fpF[c] = fpM[c] = fpS[c] = 0.0f;
+            }
 #pragma unroll
             for (int ir = 1; ir <= R; ir++) {
                 const float4 up = lds4(ctr, srow + i + ir, scol);
@@ -388,9 +409,17 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 const float upv[4] = {up.x, up.y, up.z, up.w};
                 const float dnv[4] = {dn.x, dn.y, dn.z, dn.w};
 #pragma unroll
-                for (int c = 0; c < 4; c++)
+                for (int c = 0; c < 4; c++) {
                     acc[c].ring(a, ir, w[RP + c + ir], w[RP + c - ir], upv[c], dnv[c],
                                 qv[i][c][R + ir], qv[i][c][R - ir]);
+                    if (VARDEN) {
+                        fpF[c] = ring_diff<float, MATH>(fpF[c], a.c1[ir], w[RP + c + ir],
+                                                        w[RP + c - ir]);
+                        fpM[c] = ring_diff<float, MATH>(fpM[c], a.c1[ir], upv[c], dnv[c]);
+                        fpS[c] = ring_diff<float, MATH>(fpS[c], a.c1[ir], qv[i][c][R + ir],
+                                                        qv[i][c][R - ir]);
+                    }
+                }
             }
             const int off = ((ty * PM + i) * TX + tx) * 4;
             const float4 pv = *reinterpret_cast<const float4 *>(sPrev + off);
@@ -401,10 +430,27 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
             const float pvv[4] = {pv.x, pv.y, pv.z, pv.w};
             const float c0a[4] = {cv.x, cv.y, cv.z, cv.w};
             const float qa[4] = {qd.x, qd.y, qd.z, qd.w};
+            float lap[4];
 #pragma unroll
             for (int c = 0; c < 4; c++)
-                out[i][c] = update_point<float, MATH>(acc[c].laplacian(a), qv[i][c][R], pvv[c],
-                                                      c0a[c], qa[c]);
+                lap[c] = acc[c].laplacian(a);
+            if (VARDEN) {
+                const float4 rv = *reinterpret_cast<const float4 *>(sPrev + 3 * TL::STR_FLOATS + off);
+                const float4 gF = *reinterpret_cast<const float4 *>(sPrev + 4 * TL::STR_FLOATS + off);
+                const float4 gM = *reinterpret_cast<const float4 *>(sPrev + 5 * TL::STR_FLOATS + off);
+                const float4 gS = *reinterpret_cast<const float4 *>(sPrev + 6 * TL::STR_FLOATS + off);
+                const float rva[4] = {rv.x, rv.y, rv.z, rv.w};
+                const float gFa[4] = {gF.x, gF.y, gF.z, gF.w};
+                const float gMa[4] = {gM.x, gM.y, gM.z, gM.w};
+                const float gSa[4] = {gS.x, gS.y, gS.z, gS.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    lap[c] = density_term<float, 3>(lap[c], fpS[c], gSa[c], fpM[c], gMa[c],
+                                                    fpF[c], gFa[c], a.four_h2, rva[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                out[i][c] = update_point<float, MATH>(lap[c], qv[i][c][R], pvv[c], c0a[c], qa[c]);
         }
 
         // this warp is done with the centre plane and the stream stage

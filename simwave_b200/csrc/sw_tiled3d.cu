@@ -1,26 +1,30 @@
-// Host side of the tiled 3D kernel: tensor maps, configuration table, launch.
+// Host side of the tiled 3D kernel: configuration table and launch.
 // Compiled once per radius (-DSW_RADIUS=1..10) so the build parallelises.
 #include "sw_launch.h"
 #include "sw_step_tiled3d.cuh"
 
 namespace sw {
 
-template <int R, int PM, int TX, int TY, int PF, int PS, int MINB>
+template <int R, int PM, int TX, int TY, int PF, int PS, int MINB, bool VARDEN>
 static void launch_cfg(int math, const StepArgs<float> &a, const StepMaps &maps,
                        const unsigned char *qflags, int zChunk, cudaStream_t stream)
 {
-    using TL = Tile3D<R, PM, TX, TY, PF, PS>;
+    using TL = Tile3D<R, PM, TX, TY, PF, PS, VARDEN>;
     const Grid &g = a.g;
     dim3 grid((g.nF - 2 * R + TL::BY - 1) / TL::BY, (g.nM - 2 * R + TL::BX - 1) / TL::BX,
               (g.nS - 2 * R + zChunk - 1) / zChunk);
-    auto kStrict = step3d_tiled_kernel<R, PM, TX, TY, PF, PS, MATH_STRICT, MINB>;
-    auto kFast = step3d_tiled_kernel<R, PM, TX, TY, PF, PS, MATH_FAST, MINB>;
+    auto kStrict = step3d_tiled_kernel<R, PM, TX, TY, PF, PS, MATH_STRICT, MINB, VARDEN>;
+    auto kFast = step3d_tiled_kernel<R, PM, TX, TY, PF, PS, MATH_FAST, MINB, VARDEN>;
     auto k = (math == MATH_STRICT) ? kStrict : kFast;
-    static bool configured[2] = {false, false};
-    if (!configured[math == MATH_STRICT]) {
+    // the shared-memory opt-in is per device: one bit per ordinal
+    static unsigned long long configured[2] = {0, 0};
+    int dev = 0;
+    SW_CUDA(cudaGetDevice(&dev));
+    unsigned long long &mask = configured[math == MATH_STRICT];
+    if (!(mask >> (dev & 63) & 1ull)) {
         SW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TL::SMEM_BYTES));
-        configured[math == MATH_STRICT] = true;
+        mask |= 1ull << (dev & 63);
     }
     k<<<grid, TL::THREADS, TL::SMEM_BYTES, stream>>>(a, maps, qflags, zChunk);
 }
@@ -28,23 +32,25 @@ static void launch_cfg(int math, const StepArgs<float> &a, const StepMaps &maps,
 #define SW_CFG(ID, PM, TX, TY, PF, PS, MINB)                                               \
     case ID:                                                                               \
         if (query) {                                                                       \
-            *query = {PM, TX, TY, PF, PS, MINB, Tile3D<R, PM, TX, TY, PF, PS>::SMEM_BYTES};\
+            *query = {PM, TX, TY, PF, PS, MINB,                                            \
+                      Tile3D<R, PM, TX, TY, PF, PS, VARDEN>::SMEM_BYTES};                  \
             return true;                                                                   \
         }                                                                                  \
-        launch_cfg<R, PM, TX, TY, PF, PS, MINB>(math, a, *maps, qflags, zChunk, stream);   \
+        launch_cfg<R, PM, TX, TY, PF, PS, MINB, VARDEN>(math, a, *maps, qflags, zChunk,    \
+                                                        stream);                           \
         return true;
 
-template <int R>
+// PM, TX, TY = points per thread along M, thread columns, thread rows
+// (tile = TY*PM rows x 4*TX columns); PF / PS = u_cur planes / stream
+// stages in flight; MINB = CTAs per SM the register budget is held to.
+// Thread counts are mostly kept at multiples of 4 warps (register allocation
+// granularity): 7 consumer warps + the producer warp, etc.
+template <int R, bool VARDEN>
 static bool dispatch(int cfg, TiledInfo *query, int math, const StepArgs<float> &a,
                      const StepMaps *maps, const unsigned char *qflags, int zChunk,
                      cudaStream_t stream)
 {
-    // PM, TX, TY = points per thread along M, thread columns, thread rows
-    // (tile = TY*PM rows x 4*TX columns); PF / PS = u_cur planes / stream
-    // stages in flight; MINB = CTAs per SM the register budget is held to
-    // Thread counts are kept at multiples of 4 warps (register allocation
-    // granularity): 7 consumer warps + the producer warp, etc.
-    if constexpr (R <= 5) {
+    if constexpr (!VARDEN && R <= 5) {
         switch (cfg) {
             SW_CFG(0, 1, 16, 14, 3, 3, 2)    // 14 x 64 tile, 7+1 warps
             SW_CFG(1, 2, 16, 14, 2, 3, 1)    // 28 x 64 tile, 7+1 warps
@@ -56,12 +62,28 @@ static bool dispatch(int cfg, TiledInfo *query, int math, const StepArgs<float> 
             SW_CFG(7, 1, 16, 30, 2, 3, 1)    // 30 x 64 tile, 15+1 warps
         default: return false;
         }
-    } else {
+    } else if constexpr (!VARDEN) {
         switch (cfg) {
             SW_CFG(0, 1, 16, 14, 2, 3, 1)    // 14 x 64 tile, 7+1 warps
             SW_CFG(1, 1, 16, 22, 2, 2, 1)    // 22 x 64 tile, 11+1 warps
             SW_CFG(2, 1, 32, 7, 2, 3, 1)     // 7 x 128 tile, 7+1 warps
             SW_CFG(3, 1, 16, 30, 1, 2, 1)    // 30 x 64 tile, 15+1 warps
+        default: return false;
+        }
+    } else if constexpr (R <= 5) {
+        switch (cfg) {
+            SW_CFG(0, 1, 16, 16, 2, 2, 2)    // 16 x 64 tile, 8+1 warps
+            SW_CFG(1, 1, 16, 14, 2, 2, 2)    // 14 x 64 tile, 7+1 warps
+            SW_CFG(2, 1, 16, 30, 2, 2, 1)    // 30 x 64 tile, 15+1 warps
+            SW_CFG(3, 1, 16, 22, 2, 3, 1)    // 22 x 64 tile, 11+1 warps
+        default: return false;
+        }
+    } else {
+        switch (cfg) {
+            SW_CFG(0, 1, 16, 22, 1, 2, 1)    // 22 x 64 tile, 11+1 warps
+            SW_CFG(1, 1, 16, 14, 2, 2, 1)    // 14 x 64 tile, 7+1 warps
+            SW_CFG(2, 1, 16, 16, 1, 2, 1)    // 16 x 64 tile, 8+1 warps
+            SW_CFG(3, 1, 32, 7, 1, 2, 1)     // 7 x 128 tile, 7+1 warps
         default: return false;
         }
     }
@@ -74,16 +96,20 @@ static bool dispatch(int cfg, TiledInfo *query, int math, const StepArgs<float> 
 #define SW_CAT(a, b) SW_CAT2(a, b)
 
 namespace sw {
-bool SW_CAT(tiled3d_query_r, SW_RADIUS)(int cfg, TiledInfo *info)
+bool SW_CAT(tiled3d_query_r, SW_RADIUS)(int cfg, bool varden, TiledInfo *info)
 {
     StepArgs<float> dummy{};
-    return dispatch<SW_RADIUS>(cfg, info, 0, dummy, nullptr, nullptr, 1, nullptr);
+    return varden ? dispatch<SW_RADIUS, true>(cfg, info, 0, dummy, nullptr, nullptr, 1, nullptr)
+                  : dispatch<SW_RADIUS, false>(cfg, info, 0, dummy, nullptr, nullptr, 1, nullptr);
 }
-bool SW_CAT(tiled3d_launch_r, SW_RADIUS)(int cfg, int math, const StepArgs<float> &a,
-                                         const StepMaps &maps, const unsigned char *qflags,
-                                         int zChunk, cudaStream_t stream)
+bool SW_CAT(tiled3d_launch_r, SW_RADIUS)(int cfg, bool varden, int math,
+                                         const StepArgs<float> &a, const StepMaps &maps,
+                                         const unsigned char *qflags, int zChunk,
+                                         cudaStream_t stream)
 {
-    const bool ok = dispatch<SW_RADIUS>(cfg, nullptr, math, a, &maps, qflags, zChunk, stream);
+    const bool ok =
+        varden ? dispatch<SW_RADIUS, true>(cfg, nullptr, math, a, &maps, qflags, zChunk, stream)
+               : dispatch<SW_RADIUS, false>(cfg, nullptr, math, a, &maps, qflags, zChunk, stream);
     if (ok)
         SW_CUDA(cudaGetLastError());
     return ok;

@@ -322,10 +322,11 @@ def test_u_saving(dimension, density, stride):
 # tiled 3D kernel: every radius and tile configuration against the plain kernel
 # ---------------------------------------------------------------------------
 def _tiled_vs_plain(order, tile, monkeypatch, shape=(37, 75, 150), steps=6,
-                    bc=(2, 1, 2, 1, 2, 1), math="strict"):
+                    bc=(2, 1, 2, 1, 2, 1), math="strict", density=False):
     r = order // 2
     p = problems.make_problem(
         shape=shape, space_order=order, timesteps=steps, bc=bc, seed=order,
+        density=density,
         nbl=((0, 3), (2, 2), (3, 2)), num_sources=2, src_radius=min(4, r + 1),
         num_receivers=6, rec_radius=2)
     monkeypatch.setenv("SIMWAVE_CUDA_MATH", math)
@@ -348,6 +349,27 @@ def test_tiled_kernel_every_radius(order, math, monkeypatch):
                                        math=math)
         assert np.array_equal(plain["u"], tiled["u"]), (order, cfg)
         assert np.array_equal(plain["receivers"], tiled["receivers"])
+
+
+@pytest.mark.parametrize("math", ["strict", "fast"])
+@pytest.mark.parametrize("order", [2, 4, 8, 10, 12, 16, 20])
+def test_tiled_variable_density_every_radius(order, math, monkeypatch):
+    """Variable density through the tiled kernel (streamed density
+    derivatives) against the plain kernel, nx == ny."""
+    for cfg in (0, 1, 2, 3):
+        plain, tiled = _tiled_vs_plain(order, "%d:9" % cfg, monkeypatch,
+                                       shape=(40, 150, 150), math=math,
+                                       density=True)
+        assert np.array_equal(plain["u"], tiled["u"]), (order, cfg)
+        assert np.array_equal(plain["receivers"], tiled["receivers"])
+
+
+def test_tiled_variable_density_matches_oracle():
+    p = problems.make_problem(shape=(50, 90, 90), space_order=8, density=True,
+                              timesteps=30, seed=12, smooth_density=True,
+                              nbl=((0, 5), (4, 4), (4, 4)))
+    a, b = run_pair(p)
+    assert_identical(a, b)
 
 
 @pytest.mark.parametrize("cfg", range(8))

@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-nvidia-smi topo -m > gpurun_out/topo.txt 2>&1
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-2} --master-addr 127.0.0.1 --master-port 29511 tools/slab_check.py > gpurun_out/slab_check.log 2>&1; echo "exit $?" >> gpurun_out/slab_check.log
-tail -25 gpurun_out/slab_check.log
+NG=${NG:-2}
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $NG > gpurun_out/bench_n$NG.json 2> gpurun_out/bench_n$NG.err; echo "exit $?"
+cat gpurun_out/bench_n$NG.json; tail -5 gpurun_out/bench_n$NG.err
+timeout 300 python bench.py --timesteps 300 --no-e2e --no-cpu > gpurun_out/bench_n1_short.json 2> gpurun_out/bench_n1_short.err; cat gpurun_out/bench_n1_short.json; tail -3 gpurun_out/bench_n1_short.err

@@ -9,7 +9,6 @@ Builds the workload once, then times the device-resident time loop (plan API,
 CUDA events) for every combination; prints one line per combination.
 """
 import argparse
-import ctypes
 import os
 import sys
 
@@ -17,7 +16,6 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 import bench  # noqa: E402
 import workloads  # noqa: E402
-from cuda_abi import core  # noqa: E402
 
 
 def main():
@@ -40,12 +38,7 @@ def main():
     T = p["end_timestep"]
     peak, _ = bench.measured_peak()
 
-    lib = core()
-    lib.simwave_plan_create.restype = ctypes.c_void_p
-    lib.simwave_plan_run.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
-                                     ctypes.POINTER(ctypes.c_double)]
-    lib.simwave_plan_reset.argtypes = [ctypes.c_void_p]
-    lib.simwave_plan_destroy.argtypes = [ctypes.c_void_p]
+    from simwave_b200 import slab
 
     combos = [("simple", "-", m) for m in args.math.split(",")]
     for m in args.math.split(","):
@@ -58,23 +51,18 @@ def main():
         os.environ["SIMWAVE_CUDA_KERNEL"] = "simple" if kind == "simple" else "auto"
         if kind == "tiled":
             os.environ["SIMWAVE_CUDA_TILE"] = tile
-        keep = []
-        pb = bench.make_problem_struct(p, keep)
-        plan = lib.simwave_plan_create(ctypes.byref(pb))
-        if not plan:
-            print("%-7s %-8s %-6s  FAILED: %s" % (kind, tile, math,
-                                                 lib.simwave_cuda_last_error().decode()))
+        try:
+            plan = slab.Plan(p)
+        except RuntimeError as e:
+            print("%-7s %-8s %-6s  FAILED: %s" % (kind, tile, math, e))
             continue
-        loop = ctypes.c_double()
         best = None
         for i in range(args.repeat + 1):
-            lib.simwave_plan_reset(plan)
-            if lib.simwave_plan_run(plan, 1, T, ctypes.byref(loop)) != 0:
-                print("run failed:", lib.simwave_cuda_last_error().decode())
-                break
+            plan.reset()
+            t = plan.run(1, T)
             if i > 0:
-                best = loop.value if best is None else min(best, loop.value)
-        lib.simwave_plan_destroy(plan)
+                best = t if best is None else min(best, t)
+        plan.destroy()
         if best:
             g = pts * T / best / 1e9
             print("%-7s %-8s %-6s  %8.3f ms/step  %8.2f Gpts/s  %5.1f%% of %d GB/s"

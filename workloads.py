@@ -213,10 +213,114 @@ def shot_3d(shot=0, n=512, space_order=8, timesteps=300, seed=5):
         name="shot_3d")
 
 
+def slab_3d(rank=0, world=1, planes_per_gpu=128, n=1040, space_order=16,
+            density=True, timesteps=60):
+    """C4-shaped slab workload for weak scaling: the extended grid is
+    (world*planes_per_gpu + 2r) x n x n (variable density, order 16, 40-point
+    cubic damping layers on every side but the top); this builds ONLY the
+    arrays of ``rank``'s z-slab (owned planes plus r ghost / halo planes on
+    either side), straight from closed-form model functions, so that no rank
+    ever holds the global model.  Returns the local problem dict with
+    slab_up / slab_down set (simwave_b200/slab.py)."""
+    from simwave_b200 import slab
+    dtype = np.float32
+    r = space_order // 2
+    nz = world * planes_per_gpu + 2 * r
+    lo, hi = slab.split_planes(nz, r, world)[rank]
+    a, b = lo - r, hi + r
+    h = (10.0, 10.0, 10.0)
+    nbl = ((0, 40), (40, 40), (40, 40))
+    vmin, vmax = 1500.0, 4500.0
+
+    # physical-domain index of every extended plane/row/column (edge padding
+    # = clipping the index, like SpaceModel.extended_velocity_model)
+    def phys(count, before, after):
+        idx = np.arange(count, dtype=np.float64) - (before + r)
+        return np.clip(idx, 0, count - 2 * r - before - after - 1)
+    zg = phys(nz, *nbl[0])[a:b, None, None]
+    xg = phys(n, *nbl[1])[None, :, None]
+    yg = phys(n, *nbl[2])[None, None, :]
+    bumps = (np.sin(zg / 37.0 + 0.3) * np.cos(xg / 53.0) +
+             np.sin(yg / 41.0 + 1.1) * np.cos(zg / 61.0 + xg / 97.0))
+    depth = zg / max(1.0, float(nz - 2 * r - nbl[0][1] - 1))
+    vel = (vmin + (vmax - vmin) * np.clip(0.15 + 0.6 * depth + 0.12 * bumps, 0, 1)
+           ).astype(dtype)
+    rho = None
+    if density:
+        rho = (1000.0 + 1500.0 * np.clip(0.2 + 0.5 * depth + 0.15 * np.cos(
+            xg / 45.0 + yg / 58.0 + zg / 71.0), 0, 1)).astype(dtype)
+
+    # damping mask: what np.pad(linear_ramp, end_values=nbl) builds axis by
+    # axis (SpaceModel.damping_mask), in closed form
+    def layer_depth(count, before, after):
+        idx = np.arange(count, dtype=np.float64)
+        d = np.zeros(count)
+        inner0, inner1 = r + before, count - r - after
+        d = np.where(idx < inner0, inner0 - idx, d)
+        d = np.where(idx >= inner1, idx - inner1 + 1, d)
+        d[:r] = -1
+        d[count - r:] = -1                       # halo: no damping
+        return d
+    dz = layer_depth(nz, *nbl[0])[a:b, None, None]
+    dx = layer_depth(n, *nbl[1])[None, :, None]
+    dy = layer_depth(n, *nbl[2])[None, None, :]
+    m = np.maximum(dz, 0.0) + 0 * dx + 0 * dy
+    nx_l, ny_l = float(nbl[1][0]), float(nbl[2][0])
+    m = m + (nx_l - m) * np.maximum(dx, 0.0) / nx_l
+    m = m + (ny_l - m) * np.maximum(dy, 0.0) / ny_l
+    m = np.where((dz < 0) | (dx < 0) | (dy < 0), 0.0, m)
+    damp = (0.001 * m ** 3).astype(dtype)
+
+    hf = [dtype(x) for x in h]
+    dt = dtype(fd.calculate_dt(3, space_order, hf, np.array([vmax], dtype=dtype)))
+    shape = (nz, n, n)
+    origin = np.array([nbl[0][0] + r, nbl[1][0] + r, nbl[2][0] + r], dtype=dtype)
+    size = [(m_ - 2 * r - bb - aa - 1) * s for m_, (bb, aa), s in zip(shape, nbl, h)]
+
+    def to_grid(coords):
+        return np.asarray(coords, dtype=dtype) / np.array(hf, dtype=dtype) + origin
+    src = [(20.0, size[1] / 2, size[2] / 2)]
+    rec = [(20.0, size[1] / 2, size[2] * i / 1023.0) for i in range(1024)]
+    own_lo = lo if rank > 0 else 0
+    own_hi = hi if rank < world - 1 else nz
+    tabs = {}
+    for kind, coords in (("src", src), ("rec", rec)):
+        iv, val, off = _tables(shape, to_grid(coords), 4, dtype)
+        tabs[kind] = slab._clip_tables(iv, val, off, 3, own_lo, own_hi, a)
+    wavelet = _ricker(8.0, 0.0, 4.0, max(timesteps, int(4.0 / float(dt)) + 1),
+                      dtype)[:timesteps].copy()
+    bc = [BC[x] for x in ("null_neumann", "null_dirichlet", "null_dirichlet",
+                          "null_dirichlet", "null_dirichlet", "null_dirichlet")]
+    if rank > 0:
+        bc[0] = 0
+    if rank < world - 1:
+        bc[1] = 0
+    return {
+        "name": "slab_3d",
+        "u": np.zeros((3,) + vel.shape, dtype=dtype),
+        "velocity": np.ascontiguousarray(vel),
+        "density": None if rho is None else np.ascontiguousarray(rho),
+        "damp": np.ascontiguousarray(damp), "wavelet": wavelet,
+        "coeff2": dtype(fd.half_coefficients(2, space_order)),
+        "coeff1": dtype(fd.half_coefficients(1, space_order)),
+        "bc": np.asarray(bc, dtype=np.uint64),
+        "src_intervals": tabs["src"][0], "src_values": tabs["src"][1],
+        "src_offsets": tabs["src"][2],
+        "rec_intervals": tabs["rec"][0], "rec_values": tabs["rec"][1],
+        "rec_offsets": tabs["rec"][2],
+        "receivers": np.zeros((timesteps, 1024), dtype=dtype),
+        "spacing": h, "saving_stride": 0, "dt": dt, "end_timestep": timesteps,
+        "space_order": space_order, "full_timesteps": timesteps,
+        "slab_up": int(rank > 0), "slab_down": int(rank < world - 1),
+        "global_shape": shape, "owned_planes": hi - lo,
+    }
+
+
 WORKLOADS = {
     "readme_2d": readme_2d,
     "marmousi_2d": marmousi_2d,
     "overthrust_3d": overthrust_3d,
     "variable_density_3d": variable_density_3d,
     "shot_3d": shot_3d,
+    "slab_3d": slab_3d,
 }

@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-slab", action="store_true",
                     help="skip the slab-decomposition leg")
+    ap.add_argument("--slab-only", action="store_true",
+                    help="run only the slab-decomposition leg and print it")
     ap.add_argument("--slab-planes", type=int, default=128,
                     help="owned z-planes per GPU in the slab leg")
     ap.add_argument("--slab-n", type=int, default=1040)
@@ -307,10 +309,6 @@ def run_ours(args, p, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; the CUDA backend has no "
                          "CPU fallback")
 
-    T = p["end_timestep"]
-    pts = workloads.interior_points(p)
-    bpp = workloads.bytes_per_point(p)
-
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
@@ -323,6 +321,18 @@ def run_ours(args, p, rank, world, local_rank):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    if args.slab_only:
+        res = run_slab_leg(args, rank, world, dist, barrier, max_over_ranks)
+        if rank == 0:
+            print(json.dumps({"slab": res, "n_gpus": world}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    T = p["end_timestep"]
+    pts = workloads.interior_points(p)
+    bpp = workloads.bytes_per_point(p)
 
     # ---- device-resident throughput (plan API) -----------------------------
     plan = slab.Plan(p)
@@ -452,7 +462,7 @@ def main():
         kwargs["timesteps"] = args.timesteps
     if args.workload == "shot_3d":
         kwargs["shot"] = rank
-    p = builder(**kwargs)
+    p = None if args.slab_only else builder(**kwargs)
     if args.impl == "reference":
         run_reference(args, p, rank, world)
     else:

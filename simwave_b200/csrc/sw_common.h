@@ -54,6 +54,7 @@ struct StepArgs {
     T inv_h2[3];        // 1/h2, correctly rounded (fast math mode only)
     T inv_h2_lo[3];     // 1/h2 - inv_h2 (fast math mode only)
     T four_h2[3];       // 4*h2 as the reference rounds it
+    T inv_four_h2[3];   // 1/four_h2 (fast math mode only)
     int bc[6];          // S_before,S_after,M_before,M_after,F_before,F_after
     int quirk;          // 3D variable density with nx != ny: bug-compatible x strides
     int fuse_bc;        // 1: boundary conditions written by the step kernel itself

@@ -493,6 +493,7 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
         a.inv_h2_lo[i] = std::fma(-a.inv_h2[i], a.h2[i], T(1)) / a.h2[i];
         volatile T f4 = T(4) * a.h2[i];
         a.four_h2[i] = f4;
+        a.inv_four_h2[i] = T(1) / a.four_h2[i];
     }
     const size_t *bc = pb.boundary_conditions;
     if (ndim_ == 3) {

@@ -39,7 +39,9 @@ __global__ void model_kernel(Grid g, const T *__restrict__ velocity, const T *__
 // First derivatives of the density along every axis at the interior points,
 // accumulated ring by ring exactly as the step kernels do
 // (variable_density/3d/wave.c:180-194).  They are constant in time; the tiled
-// kernel streams them instead of keeping a halo of the density.
+// kernel streams them instead of keeping a halo of the density.  In fast math
+// mode the time-invariant factor 1/(4 h^2 rho) is folded in as well
+// (density_weight), so the density itself need not be streamed.
 template <typename T, int MATH>
 __global__ void rho_gradient_kernel(const __grid_constant__ StepArgs<T> a, T *__restrict__ frF,
                                     T *__restrict__ frM, T *__restrict__ frS)
@@ -59,6 +61,12 @@ __global__ void rho_gradient_kernel(const __grid_constant__ StepArgs<T> a, T *__
         gF = ring_diff<T, MATH>(gF, a.c1[ir], d[ir], d[-ir]);
         gM = ring_diff<T, MATH>(gM, a.c1[ir], d[oM], d[-oM]);
         gS = ring_diff<T, MATH>(gS, a.c1[ir], d[oS], d[-oS]);
+    }
+    if (MATH != MATH_STRICT) {
+        const T rho = d[0];
+        gF = density_weight<T>(gF, a.inv_four_h2[AX_F], rho);
+        gM = density_weight<T>(gM, a.inv_four_h2[AX_M], rho);
+        gS = density_weight<T>(gS, a.inv_four_h2[AX_S], rho);
     }
     frF[p] = gF;
     frM[p] = gM;

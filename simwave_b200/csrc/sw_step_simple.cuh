@@ -138,8 +138,17 @@ step_simple_kernel(const __grid_constant__ StepArgs<T> a)
     }
 
     T lap = acc.laplacian(a);
-    if (VARDEN)
-        lap = density_term<T, NDIM>(lap, fpS, frS, fpM, frM, fpF, frF, a.four_h2, d[0]);
+    if (VARDEN) {
+        if (MATH == MATH_STRICT) {
+            lap = density_term<T, NDIM>(lap, fpS, frS, fpM, frM, fpF, frF, a.four_h2, d[0]);
+        } else {
+            const T rho = d[0];
+            lap = fast_density_term<T, NDIM>(
+                lap, fpS, NDIM == 3 ? density_weight<T>(frS, a.inv_four_h2[AX_S], rho) : T(0),
+                fpM, density_weight<T>(frM, a.inv_four_h2[AX_M], rho), fpF,
+                density_weight<T>(frF, a.inv_four_h2[AX_F], rho));
+        }
+    }
 
     const T val = update_point<T, MATH>(lap, uc, a.prev[p], a.c0[p], a.q[p]);
 

@@ -264,12 +264,14 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 mbar_wait(&emptyStr[st], ((j / NT) - 1) & 1);
             float *dst = streams + st * TL::STAGE_FLOATS;
             stageHasQ[st] = hasQ;
-            mbar_expect_tx(&fullStr[st], ((hasQ ? 3 : 2) + (VARDEN ? 4 : 0)) * TL::STR_BYTES);
+            constexpr int kDensityTiles = !VARDEN ? 0 : (MATH == MATH_STRICT ? 4 : 3);
+            mbar_expect_tx(&fullStr[st], ((hasQ ? 3 : 2) + kDensityTiles) * TL::STR_BYTES);
             tma_load_3d(dst, &maps.prev, &fullStr[st], g.lpad + f0, m0, z0 + j);
             tma_load_3d(dst + TL::STR_FLOATS, &maps.c0, &fullStr[st], g.lpad + f0, m0, z0 + j);
             if (VARDEN) {
-                tma_load_3d(dst + 3 * TL::STR_FLOATS, &maps.rho, &fullStr[st], g.lpad + f0, m0,
-                            z0 + j);
+                if (MATH == MATH_STRICT)    // fast math folds 1/rho into the derivatives
+                    tma_load_3d(dst + 3 * TL::STR_FLOATS, &maps.rho, &fullStr[st], g.lpad + f0,
+                                m0, z0 + j);
                 tma_load_3d(dst + 4 * TL::STR_FLOATS, &maps.frF, &fullStr[st], g.lpad + f0, m0,
                             z0 + j);
                 tma_load_3d(dst + 5 * TL::STR_FLOATS, &maps.frM, &fullStr[st], g.lpad + f0, m0,
@@ -435,7 +437,9 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
             for (int c = 0; c < 4; c++)
                 lap[c] = acc[c].laplacian(a);
             if (VARDEN) {
-                const float4 rv = *reinterpret_cast<const float4 *>(sPrev + 3 * TL::STR_FLOATS + off);
+                float4 rv = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+                if (MATH == MATH_STRICT)
+                    rv = *reinterpret_cast<const float4 *>(sPrev + 3 * TL::STR_FLOATS + off);
                 const float4 gF = *reinterpret_cast<const float4 *>(sPrev + 4 * TL::STR_FLOATS + off);
                 const float4 gM = *reinterpret_cast<const float4 *>(sPrev + 5 * TL::STR_FLOATS + off);
                 const float4 gS = *reinterpret_cast<const float4 *>(sPrev + 6 * TL::STR_FLOATS + off);
@@ -445,8 +449,11 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 const float gSa[4] = {gS.x, gS.y, gS.z, gS.w};
 #pragma unroll
                 for (int c = 0; c < 4; c++)
-                    lap[c] = density_term<float, 3>(lap[c], fpS[c], gSa[c], fpM[c], gMa[c],
-                                                    fpF[c], gFa[c], a.four_h2, rva[c]);
+                    lap[c] = (MATH == MATH_STRICT)
+                                 ? density_term<float, 3>(lap[c], fpS[c], gSa[c], fpM[c], gMa[c],
+                                                          fpF[c], gFa[c], a.four_h2, rva[c])
+                                 : fast_density_term<float, 3>(lap[c], fpS[c], gSa[c], fpM[c],
+                                                               gMa[c], fpF[c], gFa[c]);
             }
 #pragma unroll
             for (int c = 0; c < 4; c++)

@@ -59,6 +59,21 @@ struct StepArgs {
     int quirk;          // 3D variable density with nx != ny: bug-compatible x strides
     int fuse_bc;        // 1: boundary conditions written by the step kernel itself
     int denseNx, denseNy;
+    // Slab decomposition: the neighbours' u_next, shifted so that the local
+    // element index of a cell in my outermost owned planes addresses its ghost
+    // copy there (peer[0]: planes r..2r-1 -> up neighbour, peer[1]: planes
+    // nS-2r..nS-r-1 -> down neighbour); nullptr = no such neighbour / no push.
+    T *peer[2];
+
+    // where the ghost copy of a cell of plane s lives, or nullptr
+    __device__ __forceinline__ T *ghost_copy(int s) const
+    {
+        if (peer[0] != nullptr && s < 2 * g.r)
+            return peer[0];
+        if (peer[1] != nullptr && s >= g.nS - 2 * g.r)
+            return peer[1];
+        return nullptr;
+    }
 };
 
 // Source / receiver tables on the device.

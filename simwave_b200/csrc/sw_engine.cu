@@ -400,6 +400,7 @@ private:
     int *peerFlags_[2] = {nullptr, nullptr};
     int peerNS_[2] = {0, 0};
     std::vector<void *> ipcMapped_;
+    bool slabFused_ = false;   // ghost copies written by the step / source kernels themselves
     void slab_wait(size_t n);
     void slab_push(size_t n, size_t slot);
 };
@@ -466,6 +467,8 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     slabDown_ = pb.slab_down != 0;
     if ((slabUp_ || slabDown_) && (ndim_ != 3 || stride_ != 0))
         throw Error("slab decomposition needs a 3D problem with saving_stride == 0");
+    if ((slabUp_ || slabDown_) && pb.nz < 4 * (pb.space_order / 2))
+        throw Error("a slab must own at least space_order planes");
 
     SW_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     SW_CUDA(cudaEventCreate(&evBegin_));
@@ -960,6 +963,16 @@ void Plan<T>::run(size_t begin, size_t end)
         a.prev = live_[prevT_];
         a.cur = live_[curT_];
         a.next = live_[nextT_];
+        if (slabFused_) {
+            // shifted so that a local index in my outermost owned planes
+            // addresses the ghost copy on the neighbour
+            if (slabUp_)
+                a.peer[0] = peerSlot_[0][nextT_] +
+                            (long long)(peerNS_[0] - 2 * g_.r) * g_.planeStride;
+            if (slabDown_)
+                a.peer[1] = peerSlot_[1][nextT_] -
+                            (long long)(g_.nS - 2 * g_.r) * g_.planeStride;
+        }
 
         if (slabUp_ || slabDown_)
             slab_wait(n);
@@ -1108,6 +1121,11 @@ void Plan<T>::slab_connect(const void *up, const void *down)
         peerNS_[side] = d.nS;
     }
     slabConnected_ = true;
+    // ghost copies are written by the kernels themselves (overlapped with the
+    // rest of the step) unless something would bypass them: separate boundary
+    // kernels, atomically accumulated sources, or SIMWAVE_CUDA_SLAB_PUSH=copy
+    slabFused_ = args_.fuse_bc && srcMode_ != SRC_ATOMIC &&
+                 !env_is("SIMWAVE_CUDA_SLAB_PUSH", "copy");
 }
 
 // before step n reads the ghost planes of u_cur: the neighbours must have
@@ -1134,9 +1152,10 @@ void Plan<T>::slab_push(size_t n, size_t slot)
             continue;
         const long long srcPlane = (side == 0) ? r : g_.nS - 2 * r;
         const long long dstPlane = (side == 0) ? peerNS_[side] - r : 0;
-        SW_CUDA(cudaMemcpyAsync(peerSlot_[side][slot] + dstPlane * g_.planeStride - g_.lpad,
-                                mine + srcPlane * g_.planeStride - g_.lpad, r * planeBytes,
-                                cudaMemcpyDefault, stream_));
+        if (!slabFused_)
+            SW_CUDA(cudaMemcpyAsync(peerSlot_[side][slot] + dstPlane * g_.planeStride - g_.lpad,
+                                    mine + srcPlane * g_.planeStride - g_.lpad, r * planeBytes,
+                                    cudaMemcpyDefault, stream_));
         slab_publish_kernel<<<1, 1, 0, stream_>>>(peerFlags_[side], (int)n);
         check_launch("slab_publish_kernel");
     }

@@ -139,11 +139,21 @@ __device__ __forceinline__ void add_with_boundaries(const StepArgs<T> &a, T *nex
     const Grid &g = a.g;
     const int r = g.r;
     const long long p = g.at(s, m, f);
-    auto add = [&](long long idx) {
-        if (atomic)
+    // slab decomposition: a cell of my outermost owned planes is mirrored into
+    // the neighbour's ghost plane (atomic mode: the ghost copy is refreshed by
+    // the engine's plane copy instead, see Plan::slab_push)
+    T *alt = (NDIM == 3 && !atomic) ? a.ghost_copy(s) : nullptr;
+    // `samePlane`: the target lies on plane s (everything but S mirrors, which
+    // exist only at outer faces and have no ghost copy)
+    auto add = [&](long long idx, bool samePlane = true) {
+        if (atomic) {
             atomicAdd(next + idx, t);
-        else
-            next[idx] = Ops<T>::add(next[idx], t);
+        } else {
+            const T sum = Ops<T>::add(next[idx], t);
+            next[idx] = sum;
+            if (alt && samePlane)
+                alt[idx] = sum;
+        }
     };
     if (!a.fuse_bc) {
         add(p);
@@ -168,7 +178,7 @@ __device__ __forceinline__ void add_with_boundaries(const StepArgs<T> &a, T *nex
         if (NDIM == 3 && inF && inM && !inS)
             target = (s < firstS) ? a.bc[0] == 2 : a.bc[1] == 2;
         if (!target)
-            add(p);
+            add(p, inS);
         return;
     }
 
@@ -195,9 +205,9 @@ __device__ __forceinline__ void add_with_boundaries(const StepArgs<T> &a, T *nex
     if (NDIM == 3) {
         const bool zFM = zF | zMb | zMa;
         if (a.bc[0] == 2 && s > firstS && s <= firstS + r && !zFM)
-            add(p - 2 * (long long)(s - firstS) * g.planeStride);
+            add(p - 2 * (long long)(s - firstS) * g.planeStride, false);
         if (a.bc[1] == 2 && s < lastS && s >= lastS - r && !zFM && !zSb)
-            add(p + 2 * (long long)(lastS - s) * g.planeStride);
+            add(p + 2 * (long long)(lastS - s) * g.planeStride, false);
     }
 }
 

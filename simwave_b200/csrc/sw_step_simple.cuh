@@ -37,6 +37,15 @@ __device__ __forceinline__ void store_with_boundaries(const StepArgs<T> &a, T *n
     const int firstF = r, lastF = g.nF - r - 1;
     const int firstM = r, lastM = g.nM - r - 1;
     const int firstS = r, lastS = g.nS - r - 1;
+    // slab decomposition: cells of my outermost owned planes are written into
+    // the neighbour's ghost planes as well (F/M mirror cells included; S
+    // mirrors only exist at outer faces, which have no neighbour)
+    T *alt = (NDIM == 3) ? a.ghost_copy(s) : nullptr;
+    auto put = [&](long long idx, T v) {
+        next[idx] = v;
+        if (alt)
+            alt[idx] = v;
+    };
 
     const bool zFb = (a.bc[4] == 1) & (f == firstF);
     const bool zFa = (a.bc[5] == 1) & (f == lastF);
@@ -48,20 +57,20 @@ __device__ __forceinline__ void store_with_boundaries(const StepArgs<T> &a, T *n
         zSa = (a.bc[1] == 1) & (s == lastS);
     }
 
-    next[p] = (zFb | zFa | zMb | zMa | zSb | zSa) ? T(0) : val;
+    put(p, (zFb | zFa | zMb | zMa | zSb | zSa) ? T(0) : val);
 
     // F pass
     if (a.bc[4] == 2 && f > firstF && f <= firstF + r)
-        next[p - 2 * (f - firstF)] = val;
+        put(p - 2 * (f - firstF), val);
     if (a.bc[5] == 2 && f < lastF && f >= lastF - r)
-        next[p + 2 * (lastF - f)] = zFb ? T(0) : val;
+        put(p + 2 * (lastF - f), zFb ? T(0) : val);
 
     // M pass sees the F pass' zeroing
     const T vM = (zFb | zFa) ? T(0) : val;
     if (a.bc[2] == 2 && m > firstM && m <= firstM + r)
-        next[p - 2 * (long long)(m - firstM) * g.pitch] = vM;
+        put(p - 2 * (long long)(m - firstM) * g.pitch, vM);
     if (a.bc[3] == 2 && m < lastM && m >= lastM - r)
-        next[p + 2 * (long long)(lastM - m) * g.pitch] = zMb ? T(0) : vM;
+        put(p + 2 * (long long)(lastM - m) * g.pitch, zMb ? T(0) : vM);
 
     // S pass sees the F and M passes' zeroing
     if (NDIM == 3) {
@@ -152,10 +161,15 @@ step_simple_kernel(const __grid_constant__ StepArgs<T> a)
 
     const T val = update_point<T, MATH>(lap, uc, a.prev[p], a.c0[p], a.q[p]);
 
-    if (a.fuse_bc)
+    if (a.fuse_bc) {
         store_with_boundaries<T, NDIM>(a, a.next, p, s, m, f, val);
-    else
+    } else {
         a.next[p] = val;
+        if (NDIM == 3) {
+            if (T *alt = a.ghost_copy(s))
+                alt[p] = val;
+        }
+    }
 }
 
 }  // namespace sw

@@ -121,7 +121,7 @@ struct Tile3D {
 // Same semantics as store_with_boundaries, vectorised where nothing special
 // happens.  `nvalid` = how many of the four columns are interior points.
 __device__ __forceinline__ void store_row4(const StepArgs<float> &a, int s, int m, int f,
-                                           const float v[4], int nvalid)
+                                           const float v[4], int nvalid, float *alt)
 {
     const Grid &g = a.g;
     const int r = g.r;
@@ -130,6 +130,12 @@ __device__ __forceinline__ void store_row4(const StepArgs<float> &a, int s, int 
     const int firstS = r, lastS = g.nS - r - 1;
     float *next = a.next;
     const long long p = g.at(s, m, f);
+    // `alt`: ghost copy of this plane on the neighbouring slab (or nullptr)
+    auto put = [&](long long idx, float x) {
+        next[idx] = x;
+        if (alt)
+            alt[idx] = x;
+    };
 
     const bool zMb = (a.bc[2] == 1) & (m == firstM);
     const bool zMa = (a.bc[3] == 1) & (m == lastM);
@@ -145,12 +151,15 @@ __device__ __forceinline__ void store_row4(const StepArgs<float> &a, int s, int 
         own[c] = (zRow | zFb[c] | zFa[c]) ? 0.0f : v[c];
     }
     if (nvalid == 4) {
-        *reinterpret_cast<float4 *>(next + p) = make_float4(own[0], own[1], own[2], own[3]);
+        const float4 o = make_float4(own[0], own[1], own[2], own[3]);
+        *reinterpret_cast<float4 *>(next + p) = o;
+        if (alt)
+            *reinterpret_cast<float4 *>(alt + p) = o;
     } else {
 #pragma unroll
         for (int c = 0; c < 4; c++)
             if (c < nvalid)
-                next[p + c] = own[c];
+                put(p + c, own[c]);
     }
 
     const bool anyNeumann = (a.bc[0] == 2) | (a.bc[1] == 2) | (a.bc[2] == 2) | (a.bc[3] == 2) |
@@ -164,7 +173,7 @@ __device__ __forceinline__ void store_row4(const StepArgs<float> &a, int s, int 
         for (int c = 0; c < 4; c++) {
             const int fc = f + c;
             if (c < nvalid && fc > firstF && fc <= firstF + r)
-                next[p + c - 2 * (fc - firstF)] = v[c];
+                put(p + c - 2 * (fc - firstF), v[c]);
         }
     }
     if (a.bc[5] == 2 && f + 3 >= lastF - r) {
@@ -172,7 +181,7 @@ __device__ __forceinline__ void store_row4(const StepArgs<float> &a, int s, int 
         for (int c = 0; c < 4; c++) {
             const int fc = f + c;
             if (c < nvalid && fc < lastF && fc >= lastF - r)
-                next[p + c + 2 * (lastF - fc)] = zFb[c] ? 0.0f : v[c];
+                put(p + c + 2 * (lastF - fc), zFb[c] ? 0.0f : v[c]);
         }
     }
     // M pass sees the F pass' zeroing
@@ -188,9 +197,10 @@ __device__ __forceinline__ void store_row4(const StepArgs<float> &a, int s, int 
             const bool zF = zFb[c] | zFa[c];
             const float vM = zF ? 0.0f : v[c];
             if (mb)
-                next[p + c - 2 * (long long)(m - firstM) * g.pitch] = vM;
+                put(p + c - 2 * (long long)(m - firstM) * g.pitch, vM);
             if (ma)
-                next[p + c + 2 * (long long)(lastM - m) * g.pitch] = zMb ? 0.0f : vM;
+                put(p + c + 2 * (long long)(lastM - m) * g.pitch, zMb ? 0.0f : vM);
+            // S mirrors exist only at outer faces: no ghost copy there
             const float vS = (zF | zMb | zMa) ? 0.0f : v[c];
             if (sb)
                 next[p + c - 2 * (long long)(s - firstS) * g.planeStride] = vS;
@@ -464,7 +474,9 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
         release(&emptyCur[lc % NS]);
         release(&emptyStr[st]);
 
-        const bool special = edgeTile | (a.fuse_bc & ((s <= 2 * R) | (s >= lastS - R)));
+        float *alt = a.ghost_copy(s);
+        const bool special = edgeTile | (a.fuse_bc & ((s <= 2 * R) | (s >= lastS - R))) |
+                             (alt != nullptr);
         if (!special) {
 #pragma unroll
             for (int i = 0; i < PM; i++) {
@@ -478,15 +490,20 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 if (!rowValid[i])
                     continue;
                 if (a.fuse_bc) {
-                    store_row4(a, s, m0 + ty * PM + i, fMine, out[i], nvalid);
+                    store_row4(a, s, m0 + ty * PM + i, fMine, out[i], nvalid, alt);
                 } else {
                     const long long p = g.at(s, m0 + ty * PM + i, fMine);
                     if (nvalid == 4) {
-                        *reinterpret_cast<float4 *>(a.next + p) =
-                            make_float4(out[i][0], out[i][1], out[i][2], out[i][3]);
+                        const float4 o = make_float4(out[i][0], out[i][1], out[i][2], out[i][3]);
+                        *reinterpret_cast<float4 *>(a.next + p) = o;
+                        if (alt)
+                            *reinterpret_cast<float4 *>(alt + p) = o;
                     } else {
-                        for (int c = 0; c < nvalid; c++)
+                        for (int c = 0; c < nvalid; c++) {
                             a.next[p + c] = out[i][c];
+                            if (alt)
+                                alt[p + c] = out[i][c];
+                        }
                     }
                 }
             }

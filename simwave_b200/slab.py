@@ -36,10 +36,11 @@ DESC_BYTES = 512
 
 def split_planes(nz, radius, world):
     """Owned interior plane ranges [(lo, hi), ...] (global indices, hi
-    exclusive), as even as possible, every slab at least 2*radius+2 planes so
-    that the fused boundary logic applies (extent >= 3r+2 with ghosts)."""
+    exclusive), as even as possible.  Every slab owns at least 2*radius planes:
+    the planes it hands to its upper and to its lower neighbour must not
+    overlap."""
     interior = nz - 2 * radius
-    if world < 1 or interior // world < max(1, radius + 2):
+    if world < 1 or interior // world < 2 * radius:
         raise ValueError("too many slabs for %d interior planes" % interior)
     base, extra = divmod(interior, world)
     ranges, lo = [], radius

@@ -55,8 +55,9 @@ def main():
         dist.all_gather_object(out, b)
         return out
 
-    for math in ("strict", "fast"):
+    for math, push in (("strict", "fused"), ("fast", "fused"), ("strict", "copy")):
         os.environ["SIMWAVE_CUDA_MATH"] = math
+        os.environ["SIMWAVE_CUDA_SLAB_PUSH"] = push
         for shape, order, density, steps, bc in CASES:
             p = problems.make_problem(
                 shape=shape, space_order=order, density=density,
@@ -92,9 +93,9 @@ def main():
                 es = rel_l2(rec.cpu().numpy(), single["receivers"])
                 ok = same and eu <= 1e-5 and er <= 1e-5
                 failures += 0 if ok else 1
-                print("%-6s %s so%d %s T=%d on %d slabs: wavefield %s single-GPU; "
+                print("%-6s/%-5s %s so%d %s T=%d on %d slabs: wavefield %s single-GPU; "
                       "vs CPU oracle rel-L2 u %.2e rec %.2e; rec vs single-GPU %.2e  %s"
-                      % (math, "x".join(map(str, shape)), order,
+                      % (math, push, "x".join(map(str, shape)), order,
                          "var" if density else "const", steps, world,
                          "bit-identical to" if same else "DIFFERS from",
                          eu, er, es, "OK" if ok else "FAIL"), flush=True)

@@ -218,6 +218,13 @@ int simwave_cuda_last_timing_ex(double *out, int n);
 /* Number of kernels launched by the last forward()/plan run on this thread. */
 unsigned long long simwave_cuda_last_launch_count(void);
 
+/* Device buffers and pinned staging buffers are kept between calls (a survey
+ * calls forward() once per shot with the same shapes); this hands every cached
+ * block back to the driver.  The cache is bounded by half of the device memory
+ * and 512 MiB of pinned memory, is emptied automatically when an allocation
+ * fails, and is off altogether with SIMWAVE_CUDA_CACHE=0. */
+void simwave_cuda_release_cache(void);
+
 /*
  * Plan API: a problem kept resident on one device.
  *

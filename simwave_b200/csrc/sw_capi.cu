@@ -1,5 +1,7 @@
 // extern "C" surface of libsimwave_b200.so (declared in include/simwave_cuda.h)
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sw_engine.h"
@@ -38,6 +40,11 @@ static double run_forward(const simwave_problem &pb, size_t begin, size_t end)
         t.teardown = wall() - t1;
         t.total = wall() - t0;
         last_timing() = t;
+        if (std::getenv("SIMWAVE_CUDA_VERBOSE"))
+            std::fprintf(stderr,
+                         "simwave_b200: forward %.3f s = upload %.3f + run %.3f (device loop %.3f) "
+                         "+ download %.3f + teardown %.3f\n",
+                         t.total, t.h2d, t.run_wall, t.loop, t.d2h, t.teardown);
         return t.total;
     } catch (const std::exception &e) {
         set_last_error(e.what());
@@ -97,6 +104,8 @@ int simwave_cuda_last_timing_ex(double *out, int n)
         out[i] = v[i];
     return 6;
 }
+
+void simwave_cuda_release_cache(void) { sw::release_caches(); }
 
 unsigned long long simwave_cuda_last_launch_count(void) { return sw::last_timing().launches; }
 

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 
 #include <type_traits>
 
@@ -28,6 +29,28 @@ static double wall()
     using namespace std::chrono;
     return duration<double>(steady_clock::now().time_since_epoch()).count();
 }
+
+// phase log of the upload (printed under SIMWAVE_CUDA_VERBOSE)
+struct PhaseLog {
+    bool on;
+    double t;
+    std::string out;
+    PhaseLog() : on(std::getenv("SIMWAVE_CUDA_VERBOSE") != nullptr), t(wall()) {}
+    void mark(const char *what)
+    {
+        if (!on) return;
+        const double now = wall();
+        char buf[96];
+        std::snprintf(buf, sizeof(buf), " %s %.1f ms;", what, 1e3 * (now - t));
+        out += buf;
+        t = now;
+    }
+    ~PhaseLog()
+    {
+        if (on && !out.empty())
+            std::fprintf(stderr, "simwave_b200: upload phases:%s\n", out.c_str());
+    }
+};
 
 static thread_local Timing g_lastTiming;
 Timing &last_timing() { return g_lastTiming; }
@@ -51,17 +74,168 @@ Options Options::from_env()
     return o;
 }
 
+// ---------------------------------------------------------------------------
+// allocation caches
+// ---------------------------------------------------------------------------
+namespace {
+struct Caches {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> device;   // (ordinal, bytes) -> block
+    std::map<int, size_t> deviceBytes, deviceLimit;
+    std::multimap<size_t, void *> pinned;
+    size_t pinnedBytes = 0;
+    bool enabled = !env_is("SIMWAVE_CUDA_CACHE", "0");
+};
+// never destroyed: no CUDA calls during static destruction
+Caches &caches()
+{
+    static Caches *c = new Caches;
+    return *c;
+}
+
+void *device_take(size_t bytes, int *deviceOut)
+{
+    int dev = 0;
+    SW_CUDA(cudaGetDevice(&dev));
+    *deviceOut = dev;
+    Caches &c = caches();
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.device.find(std::make_pair(dev, bytes));
+        if (it != c.device.end()) {
+            void *p = it->second;
+            c.device.erase(it);
+            c.deviceBytes[dev] -= bytes;
+            return p;
+        }
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        release_caches();
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess)
+        throw Error(std::string("cudaMalloc of ") + std::to_string(bytes) +
+                    " bytes failed: " + cudaGetErrorString(e));
+    return p;
+}
+
+void device_give(void *p, size_t bytes, int dev)
+{
+    Caches &c = caches();
+    if (c.enabled) {
+        std::lock_guard<std::mutex> lk(c.mu);
+        if (!c.deviceLimit.count(dev)) {
+            size_t freeB = 0, totalB = 0;
+            int cur = 0;
+            cudaGetDevice(&cur);
+            if (cur == dev && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess)
+                c.deviceLimit[dev] = totalB / 2;
+            else
+                cudaGetLastError();
+        }
+        const size_t limit = c.deviceLimit.count(dev) ? c.deviceLimit[dev] : 0;
+        if (c.deviceBytes[dev] + bytes <= limit) {
+            c.device.emplace(std::make_pair(dev, bytes), p);
+            c.deviceBytes[dev] += bytes;
+            return;
+        }
+    }
+    cudaFree(p);
+}
+}  // namespace
+
+void *pinned_take(size_t bytes)
+{
+    Caches &c = caches();
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.pinned.find(bytes);
+        if (it != c.pinned.end()) {
+            void *p = it->second;
+            c.pinned.erase(it);
+            c.pinnedBytes -= bytes;
+            return p;
+        }
+    }
+    void *p = nullptr;
+    SW_CUDA(cudaMallocHost(&p, bytes));
+    return p;
+}
+
+void pinned_give(void *p, size_t bytes)
+{
+    Caches &c = caches();
+    if (c.enabled) {
+        std::lock_guard<std::mutex> lk(c.mu);
+        if (c.pinnedBytes + bytes <= (512u << 20)) {
+            c.pinned.emplace(bytes, p);
+            c.pinnedBytes += bytes;
+            return;
+        }
+    }
+    cudaFreeHost(p);
+}
+
+void release_caches()
+{
+    Caches &c = caches();
+    std::lock_guard<std::mutex> lk(c.mu);
+    for (auto &kv : c.device)
+        cudaFree(kv.second);
+    c.device.clear();
+    c.deviceBytes.clear();
+    for (auto &kv : c.pinned)
+        cudaFreeHost(kv.second);
+    c.pinned.clear();
+    c.pinnedBytes = 0;
+    cudaGetLastError();
+}
+
+bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+void parallel_memcpy(void *dst, const void *src, size_t bytes)
+{
+    const size_t kMinPerThread = 4u << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t n = std::min<size_t>(std::min<size_t>(hw ? hw : 1, 4), bytes / kMinPerThread);
+    if (n <= 1) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t part = (bytes / n + 63) & ~size_t(63);
+    for (size_t t = 1; t < n; t++) {
+        const size_t b = t * part, e = std::min(bytes, b + part);
+        if (b < e)
+            th.emplace_back([=] { std::memcpy((char *)dst + b, (const char *)src + b, e - b); });
+    }
+    std::memcpy(dst, src, std::min(part, bytes));
+    for (auto &x : th)
+        x.join();
+}
+
 void DeviceBuffer::alloc(size_t bytes)
 {
     release();
-    SW_CUDA(cudaMalloc(&ptr_, bytes ? bytes : 1));
+    ptr_ = device_take(bytes ? bytes : 1, &device_);
     bytes_ = bytes;
 }
 
 void DeviceBuffer::release()
 {
     if (ptr_)
-        cudaFree(ptr_);
+        device_give(ptr_, bytes_ ? bytes_ : 1, device_);
     ptr_ = nullptr;
     bytes_ = 0;
 }
@@ -72,10 +246,8 @@ void DeviceBuffer::release()
 HostDrain::HostDrain(int device, size_t chunkBytes) : device_(device), chunkBytes_(chunkBytes)
 {
     SW_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-        SW_CUDA(cudaMallocHost(&pinned_[i], chunkBytes_));
+    for (int i = 0; i < 2; i++)
         SW_CUDA(cudaEventCreateWithFlags(&copied_[i], cudaEventDisableTiming));
-    }
     thread_ = std::thread([this] { worker(); });
 }
 
@@ -89,7 +261,7 @@ HostDrain::~HostDrain()
     if (thread_.joinable())
         thread_.join();
     for (int i = 0; i < 2; i++) {
-        if (pinned_[i]) cudaFreeHost(pinned_[i]);
+        if (pinned_[i]) pinned_give(pinned_[i], chunkBytes_);
         if (copied_[i]) cudaEventDestroy(copied_[i]);
     }
     if (stream_) cudaStreamDestroy(stream_);
@@ -115,6 +287,13 @@ void HostDrain::wait_idle()
     }
 }
 
+void HostDrain::ensure_staging()
+{
+    for (int i = 0; i < 2; i++)
+        if (!pinned_[i])
+            pinned_[i] = pinned_take(chunkBytes_);
+}
+
 void HostDrain::worker()
 {
     cudaSetDevice(device_);
@@ -131,6 +310,16 @@ void HostDrain::worker()
         }
         try {
             SW_CUDA(cudaEventSynchronize(job.ready));
+            if (is_pinned_host(job.dst)) {
+                // page-locked destination: one strided DMA, no staging
+                SW_CUDA(cudaMemcpy2DAsync(job.dst, job.rowBytes, job.src, job.srcPitchBytes,
+                                          job.rowBytes, job.rows, cudaMemcpyDeviceToHost,
+                                          stream_));
+                SW_CUDA(cudaStreamSynchronize(stream_));
+                job.rows = 0;
+            } else {
+                ensure_staging();
+            }
             const size_t rowsPerChunk = std::max<size_t>(1, chunkBytes_ / job.rowBytes);
             const size_t chunks = (job.rows + rowsPerChunk - 1) / rowsPerChunk;
             auto issue = [&](size_t c) {
@@ -150,8 +339,8 @@ void HostDrain::worker()
                     issue(c + 1);  // overlaps with the memcpy below
                 const size_t r0 = c * rowsPerChunk;
                 const size_t nr = std::min(rowsPerChunk, job.rows - r0);
-                std::memcpy((char *)job.dst + r0 * job.rowBytes, pinned_[c & 1],
-                            nr * job.rowBytes);
+                parallel_memcpy((char *)job.dst + r0 * job.rowBytes, pinned_[c & 1],
+                                nr * job.rowBytes);
             }
         } catch (const std::exception &e) {
             std::lock_guard<std::mutex> lk(mu_);
@@ -179,7 +368,8 @@ static bool all_zero(const void *p, size_t bytes)
 {
     const size_t words = bytes / 8;
     const uint64_t *w = (const uint64_t *)p;
-    const int nthreads = (bytes > (64u << 20)) ? 8 : 1;
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nthreads = (bytes > (64u << 20)) ? (int)std::min(16u, std::max(3u, hw) - 1) : 1;
     std::vector<char> nz(nthreads, 0);
     auto scan = [&](int t) {
         const size_t b = words * t / nthreads, e = words * (t + 1) / nthreads;
@@ -338,6 +528,7 @@ private:
     void retire(size_t slot, bool keep);
     void retire_below(size_t bound);
     void upload_dense(const T *host, T *pitchedBase);
+    void h2d(void *dst, const void *src, size_t bytes);
     void launch_step(const StepArgs<T> &a);
     void launch_sources(const StepArgs<T> &a, size_t n);
     void launch_receivers(const T *cur, size_t n);
@@ -392,6 +583,11 @@ private:
 
     std::unique_ptr<HostDrain> drain_;
 
+    // pinned staging for uploads from pageable memory
+    void *upPinned_[2] = {nullptr, nullptr};
+    cudaEvent_t upDone_[2] = {nullptr, nullptr};
+    static constexpr size_t kUpChunk = 32u << 20;
+
     // slab decomposition: neighbours' slot buffers and flag words, mapped
     // through CUDA IPC; flags_ = {from up, from down, error}
     bool slabUp_ = false, slabDown_ = false, slabConnected_ = false;
@@ -420,6 +616,7 @@ template <typename T>
 Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
 {
     const double t0 = wall();
+    PhaseLog phases;
     ndim_ = pb.ndim;
     varden_ = pb.density != nullptr;
     if (ndim_ != 2 && ndim_ != 3)
@@ -463,6 +660,21 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     nrec_ = pb.num_receivers;
     if (numSlots_ < 3)
         throw Error("u must hold at least 3 slots");
+    // Which of the caller's slots start as zeros (those are never uploaded):
+    // scanned on helper threads while the model goes up.  A page-locked `u`
+    // with only the three rotating slots is cheaper to upload outright (one
+    // DMA at link speed) than to read once with the CPU.
+    slotZero_.assign(numSlots_, 0);
+    std::future<void> zeroScan;
+    if (!(numSlots_ == 3 && is_pinned_host(hostU_)))
+        zeroScan = std::async(std::launch::async, [this] {
+            if (all_zero(hostU_, numSlots_ * denseCells_ * sizeof(T))) {
+                std::fill(slotZero_.begin(), slotZero_.end(), 1);
+            } else {
+                for (size_t s = 0; s < numSlots_; s++)
+                    slotZero_[s] = all_zero(hostU_ + s * denseCells_, denseCells_ * sizeof(T));
+            }
+        });
     slabUp_ = pb.slab_up != 0;
     slabDown_ = pb.slab_down != 0;
     if ((slabUp_ || slabDown_) && (ndim_ != 3 || stride_ != 0))
@@ -473,6 +685,7 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     SW_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     SW_CUDA(cudaEventCreate(&evBegin_));
     SW_CUDA(cudaEventCreate(&evEnd_));
+    phases.mark("context+stream");
 
     // ---- static part of the step arguments ------------------------------
     StepArgs<T> &a = args_;
@@ -524,10 +737,8 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     new_field(q_);
     stage_.alloc(2 * denseCells_ * sizeof(T));
     T *stageA = stage_.as<T>(), *stageB = stage_.as<T>() + denseCells_;
-    SW_CUDA(cudaMemcpyAsync(stageA, pb.velocity, denseCells_ * sizeof(T),
-                            cudaMemcpyHostToDevice, stream_));
-    SW_CUDA(cudaMemcpyAsync(stageB, pb.damp, denseCells_ * sizeof(T),
-                            cudaMemcpyHostToDevice, stream_));
+    h2d(stageA, pb.velocity, denseCells_ * sizeof(T));
+    h2d(stageB, pb.damp, denseCells_ * sizeof(T));
     model_kernel<T><<<row_grid(g), 256, 0, stream_>>>(g, stageA, stageB, dt, dtsq,
                                                       field_base(c0_), field_base(q_));
     check_launch("model_kernel");
@@ -538,6 +749,7 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     a.c0 = field_base(c0_);
     a.q = field_base(q_);
     a.rho = varden_ ? field_base(rho_) : nullptr;
+    phases.mark("model alloc+enqueue");
 
     // ---- wavelet and tables -------------------------------------------------
     auto to_device = [&](DeviceBuffer &b, const void *src, size_t bytes) {
@@ -606,18 +818,15 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     else
         stepSimple_ = varden_ ? &launch_step_simple<T, 2, true> : &launch_step_simple<T, 2, false>;
 
+    phases.mark("tables");
     choose_tiling();
+    phases.mark("tiling");
 
-    // ---- which of the caller's slots start as zeros ----------------------------
-    slotZero_.assign(numSlots_, 0);
-    if (all_zero(hostU_, numSlots_ * denseCells_ * sizeof(T))) {
-        std::fill(slotZero_.begin(), slotZero_.end(), 1);
-    } else {
-        for (size_t s = 0; s < numSlots_; s++)
-            slotZero_[s] = all_zero(hostU_ + s * denseCells_, denseCells_ * sizeof(T));
-    }
-
+    if (zeroScan.valid())
+        zeroScan.get();
+    phases.mark("zero scan of u");
     drain_.reset(new HostDrain(device_, 32u << 20));
+    phases.mark("drain thread+pinned");
     if (slabUp_ || slabDown_) {
         // the three slots stay resident so that the neighbours can map them
         for (size_t s = 0; s < 3; s++)
@@ -626,6 +835,7 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
         SW_CUDA(cudaMemsetAsync(slabFlags_.get(), 0, slabFlags_.bytes(), stream_));
     }
     SW_CUDA(cudaStreamSynchronize(stream_));
+    phases.mark("sync");
     timing.h2d = wall() - t0;
 }
 
@@ -636,6 +846,10 @@ Plan<T>::~Plan()
     if (stream_) {
         cudaStreamSynchronize(stream_);
         cudaStreamDestroy(stream_);
+    }
+    for (int i = 0; i < 2; i++) {
+        if (upPinned_[i]) pinned_give(upPinned_[i], kUpChunk);
+        if (upDone_[i]) cudaEventDestroy(upDone_[i]);
     }
     for (void *p : ipcMapped_)
         cudaIpcCloseMemHandle(p);
@@ -650,13 +864,40 @@ void Plan<T>::new_field(DeviceBuffer &b)
     SW_CUDA(cudaMemsetAsync(b.get(), 0, fieldBytes_, stream_));
 }
 
+// Host -> device copy on the compute stream.  Page-locked sources go as one
+// DMA; pageable ones are staged through two pinned buffers filled by a few
+// threads, so the copy runs at link speed instead of the driver's
+// single-threaded pageable path.
+template <typename T>
+void Plan<T>::h2d(void *dst, const void *src, size_t bytes)
+{
+    if (bytes < (8u << 20) || is_pinned_host(src)) {
+        SW_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_));
+        return;
+    }
+    for (int i = 0; i < 2; i++) {
+        if (!upPinned_[i]) {
+            upPinned_[i] = pinned_take(kUpChunk);
+            SW_CUDA(cudaEventCreateWithFlags(&upDone_[i], cudaEventDisableTiming));
+        }
+    }
+    size_t c = 0;
+    for (size_t off = 0; off < bytes; off += kUpChunk, c++) {
+        const size_t n = std::min(kUpChunk, bytes - off);
+        SW_CUDA(cudaEventSynchronize(upDone_[c & 1]));   // staging buffer free again
+        parallel_memcpy(upPinned_[c & 1], (const char *)src + off, n);
+        SW_CUDA(cudaMemcpyAsync((char *)dst + off, upPinned_[c & 1], n, cudaMemcpyHostToDevice,
+                                stream_));
+        SW_CUDA(cudaEventRecord(upDone_[c & 1], stream_));
+    }
+}
+
 template <typename T>
 void Plan<T>::upload_dense(const T *host, T *pitchedBase)
 {
     if (!stage_.get())
         stage_.alloc(2 * denseCells_ * sizeof(T));
-    SW_CUDA(cudaMemcpyAsync(stage_.get(), host, denseCells_ * sizeof(T),
-                            cudaMemcpyHostToDevice, stream_));
+    h2d(stage_.get(), host, denseCells_ * sizeof(T));
     pack_kernel<T><<<row_grid(g_), 256, 0, stream_>>>(g_, stage_.as<T>(), pitchedBase);
     check_launch("pack_kernel");
 }
@@ -751,7 +992,7 @@ void Plan<T>::choose_tiling()
             return;
         const int r = g_.r;
         // default configuration, overridable as SIMWAVE_CUDA_TILE=<cfg>[:<zchunk>]
-        int cfg = (r <= 5 && !varden_) ? 6 : 0;
+        int cfg = 0;
         int zchunk = 0;
         if (const char *e = std::getenv("SIMWAVE_CUDA_TILE")) {
             cfg = std::atoi(e);

@@ -38,10 +38,17 @@ public:
     ~DeviceBuffer() { release(); }
     DeviceBuffer(const DeviceBuffer &) = delete;
     DeviceBuffer &operator=(const DeviceBuffer &) = delete;
-    DeviceBuffer(DeviceBuffer &&o) noexcept : ptr_(o.ptr_), bytes_(o.bytes_) { o.ptr_ = nullptr; o.bytes_ = 0; }
+    DeviceBuffer(DeviceBuffer &&o) noexcept : ptr_(o.ptr_), bytes_(o.bytes_), device_(o.device_)
+    {
+        o.ptr_ = nullptr; o.bytes_ = 0;
+    }
     DeviceBuffer &operator=(DeviceBuffer &&o) noexcept
     {
-        if (this != &o) { release(); ptr_ = o.ptr_; bytes_ = o.bytes_; o.ptr_ = nullptr; o.bytes_ = 0; }
+        if (this != &o) {
+            release();
+            ptr_ = o.ptr_; bytes_ = o.bytes_; device_ = o.device_;
+            o.ptr_ = nullptr; o.bytes_ = 0;
+        }
         return *this;
     }
     void alloc(size_t bytes);
@@ -53,7 +60,23 @@ public:
 private:
     void *ptr_ = nullptr;
     size_t bytes_ = 0;
+    int device_ = 0;
 };
+
+// Process-wide caches behind DeviceBuffer and the pinned staging buffers: a
+// survey calls `forward` once per shot with the same shapes, and cudaMalloc /
+// cudaFree / cudaMallocHost of GB-sized blocks cost more than the copies they
+// serve.  Blocks are handed back to the driver when an allocation fails, when
+// the cache would exceed half of the device memory, through
+// simwave_cuda_release_cache(), or never (SIMWAVE_CUDA_CACHE=0 disables it).
+void *pinned_take(size_t bytes);
+void pinned_give(void *p, size_t bytes);
+void release_caches();
+
+// true if [p, p+1) is page-locked host memory known to the CUDA driver
+bool is_pinned_host(const void *p);
+// memcpy split over a few threads (pageable <-> pinned staging copies)
+void parallel_memcpy(void *dst, const void *src, size_t bytes);
 
 // Drains pitched device fields into dense caller memory on a side stream:
 // device -> pinned staging (cudaMemcpy2DAsync, double buffered) -> memcpy into
@@ -77,6 +100,7 @@ public:
     void wait_idle();           // rethrows a worker failure
 private:
     void worker();
+    void ensure_staging();
     int device_;
     size_t chunkBytes_;
     void *pinned_[2] = {nullptr, nullptr};

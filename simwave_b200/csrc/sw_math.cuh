@@ -221,6 +221,113 @@ struct Stencil {
 template <typename T, int MATH>
 using Stencil3 = Stencil<T, 3, MATH>;
 
+// ---------------------------------------------------------------------------
+// Packed pairs.  sm_100a has two-wide float32 instructions (FADD2 / FMUL2 /
+// FFMA2 on an aligned register pair): each lane is an ordinary IEEE
+// round-to-nearest operation, so a pair of points goes through exactly the
+// scalar helpers above, lane by lane, at half the issue slots.  Operations
+// without a packed form (divisions, the double-promoted leapfrog of STRICT
+// mode) are done per lane with the scalar helpers.
+// ---------------------------------------------------------------------------
+struct Pair {
+    static __device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
+    static __device__ __forceinline__ float2 mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+    // ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 although
+    // both carry an explicit rounding; the scalar forms are left alone.
+    // STRICT mode therefore multiplies lane by lane.
+    static __device__ __forceinline__ float2 mul_exact(float2 a, float2 b)
+    {
+        return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+    }
+    static __device__ __forceinline__ float2 add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+    // a - b: b * -1 is exact, so this is the one rounding of a scalar subtract
+    static __device__ __forceinline__ float2 sub(float2 a, float2 b)
+    {
+        return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a);
+    }
+    static __device__ __forceinline__ float2 fma(float2 a, float2 b, float2 c)
+    {
+        return __ffma2_rn(a, b, c);
+    }
+};
+
+template <int MATH>
+__device__ __forceinline__ float2 ring_sum2(float2 acc, float c, float2 a, float2 b)
+{
+    if (MATH == MATH_STRICT)
+        return Pair::add(acc, Pair::mul_exact(Pair::bc(c), Pair::add(a, b)));
+    return Pair::fma(Pair::bc(c), Pair::add(a, b), acc);
+}
+
+template <int MATH>
+__device__ __forceinline__ float2 ring_diff2(float2 acc, float c, float2 a, float2 b)
+{
+    if (MATH == MATH_STRICT)
+        return Pair::add(acc, Pair::mul_exact(Pair::bc(c), Pair::sub(a, b)));
+    return Pair::fma(Pair::bc(c), Pair::sub(a, b), acc);
+}
+
+// Stencil<float, 3, MATH> on two points at once
+template <int MATH>
+struct Stencil3x2 {
+    float2 sF, sM, sS;
+    __device__ __forceinline__ void begin(const StepArgs<float> &a, float2 u)
+    {
+        sF = sM = sS = (MATH == MATH_STRICT) ? Pair::mul_exact(Pair::bc(a.c2[0]), u)
+                                             : Pair::mul(Pair::bc(a.c2[0]), u);
+    }
+    __device__ __forceinline__ void ringF(const StepArgs<float> &a, int ir, float2 p, float2 m)
+    {
+        sF = ring_sum2<MATH>(sF, a.c2[ir], p, m);
+    }
+    __device__ __forceinline__ void ringM(const StepArgs<float> &a, int ir, float2 p, float2 m)
+    {
+        sM = ring_sum2<MATH>(sM, a.c2[ir], p, m);
+    }
+    __device__ __forceinline__ void ringS(const StepArgs<float> &a, int ir, float2 p, float2 m)
+    {
+        sS = ring_sum2<MATH>(sS, a.c2[ir], p, m);
+    }
+    __device__ __forceinline__ float2 laplacian(const StepArgs<float> &a) const
+    {
+        if (MATH == MATH_STRICT)
+            return make_float2(
+                sw::laplacian<float, 3, MATH>(sS.x, sM.x, sF.x, a.h2, a.inv_h2),
+                sw::laplacian<float, 3, MATH>(sS.y, sM.y, sF.y, a.h2, a.inv_h2));
+        float2 lo = Pair::mul(sF, Pair::bc(a.inv_h2_lo[AX_F]));
+        lo = Pair::fma(sM, Pair::bc(a.inv_h2_lo[AX_M]), lo);
+        lo = Pair::fma(sS, Pair::bc(a.inv_h2_lo[AX_S]), lo);
+        float2 t = Pair::fma(sF, Pair::bc(a.inv_h2[AX_F]), lo);
+        t = Pair::fma(sM, Pair::bc(a.inv_h2[AX_M]), t);
+        t = Pair::fma(sS, Pair::bc(a.inv_h2[AX_S]), t);
+        return t;
+    }
+};
+
+// fast_density_term<float, 3> on two points
+__device__ __forceinline__ float2 fast_density_term2(float2 value, float2 fpS, float2 gS,
+                                                     float2 fpM, float2 gM, float2 fpF, float2 gF)
+{
+    float2 t = Pair::mul(fpF, gF);
+    t = Pair::fma(fpM, gM, t);
+    t = Pair::fma(fpS, gS, t);
+    return Pair::sub(value, t);
+}
+
+// update_point<float, MATH> on two points.  DAMPED == false: the caller knows
+// q == 0 for both points (no absorbing layer inside this tile and plane).
+template <int MATH, bool DAMPED>
+__device__ __forceinline__ float2 update_pair(float2 lap, float2 u, float2 prev, float2 c0,
+                                              float2 q)
+{
+    if (MATH == MATH_STRICT || DAMPED)
+        return make_float2(update_point<float, MATH>(lap.x, u.x, prev.x, c0.x, DAMPED ? q.x : 0.0f),
+                           update_point<float, MATH>(lap.y, u.y, prev.y, c0.y, DAMPED ? q.y : 0.0f));
+    // fma(lap, c0, fma(2, u, -prev)), both lanes
+    const float2 t = Pair::fma(Pair::bc(2.0f), u, make_float2(-prev.x, -prev.y));
+    return Pair::fma(lap, c0, t);
+}
+
 // source increment: dt^2/slowness * kws * wavelet / D           (3d/wave.c:277)
 template <typename T>
 __device__ __forceinline__ T source_term(T c0, T q, T kws, T w)

@@ -210,7 +210,34 @@ __device__ __forceinline__ void store_row4(const StepArgs<float> &a, int s, int 
     }
 }
 
-template <int R, int PM, int TX, int TY, int PF, int PS, int MATH, int MINB, bool VARDEN>
+// The rare store: rows of planes near an S face, of planes with a ghost copy
+// on a neighbouring slab, or of tiles on a Neumann M/F face.  Kept out of
+// line so the unrolled plane loop stays small.
+static __device__ __noinline__ void store_row_special(const StepArgs<float> &a, int s, int m, int f,
+                                               float4 o, int nvalid)
+{
+    float *alt = a.ghost_copy(s);
+    const float o4[4] = {o.x, o.y, o.z, o.w};
+    if (a.fuse_bc) {
+        store_row4(a, s, m, f, o4, nvalid, alt);
+        return;
+    }
+    const long long p = a.g.at(s, m, f);
+    if (nvalid == 4) {
+        *reinterpret_cast<float4 *>(a.next + p) = o;
+        if (alt)
+            *reinterpret_cast<float4 *>(alt + p) = o;
+    } else {
+        for (int c = 0; c < nvalid; c++) {
+            a.next[p + c] = o4[c];
+            if (alt)
+                alt[p + c] = o4[c];
+        }
+    }
+}
+
+template <int R, int PM, int TX, int TY, int PF, int PS, int MATH, int MINB, bool VARDEN,
+          int UNR>
 __global__ void __launch_bounds__(TX *TY + 32, MINB)
 step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                     const __grid_constant__ StepMaps maps,
@@ -344,8 +371,9 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
             mbar_arrive(bar);
     };
 
-    // register queue over S: qv[i][c][k] holds plane (centre - R + k)
-    float qv[PM][4][Q];
+    // register queue over S: qv[i][h][k] holds plane (centre - R + k) of the
+    // point pair h (columns 2h, 2h+1) of row i
+    float2 qv[PM][2][Q];
 
     // prime the queue with planes z0-R .. z0+R-1.  The first R of them are
     // never centre planes, so their slots go back as soon as every thread of
@@ -358,13 +386,54 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
         for (int i = 0; i < PM; i++) {
             const float4 v = lds4(slot, srow + i, scol);
             // positions 1..2R: the loop's shift brings them to 0..2R-1
-            qv[i][0][l + 1] = v.x; qv[i][1][l + 1] = v.y;
-            qv[i][2][l + 1] = v.z; qv[i][3][l + 1] = v.w;
+            qv[i][0][l + 1] = make_float2(v.x, v.y);
+            qv[i][1][l + 1] = make_float2(v.z, v.w);
         }
         if (l < R)
             release(&emptyCur[l % NS]);
     }
 
+    // Store tiers.  Planes [jPlainLo, jPlainHi) of this CTA lie clear of the
+    // S faces and have no ghost copy; inside that range an interior tile
+    // stores one float4 per row (tier 0), an edge tile without Neumann M/F
+    // faces masks Dirichlet cells and overhanging rows / columns itself
+    // (tier 1); everything else goes through store_row_special (tier 2).
+    int jPlainLo, jPlainHi;
+    {
+        int sLo = a.fuse_bc ? 2 * R + 1 : 0;               // first plane with s > 2R
+        int sHi = a.fuse_bc ? lastS - R : g.nS;            // first plane with s >= lastS - R
+        if (a.peer[0] != nullptr) sLo = max(sLo, 2 * R);
+        if (a.peer[1] != nullptr) sHi = min(sHi, g.nS - 2 * R);
+        jPlainLo = max(sLo - z0, 0);
+        jPlainHi = min(sHi - z0, planes);
+    }
+    const bool mfNeumann = a.fuse_bc && ((a.bc[2] == 2) | (a.bc[3] == 2) | (a.bc[4] == 2) |
+                                         (a.bc[5] == 2));
+    const int tileTier = !edgeTile ? 0 : (mfNeumann ? 2 : 1);
+    if (tileTier == 2)
+        jPlainHi = jPlainLo;
+    // tier 1: bit c of keep[i] = column c of row i is an interior point that
+    // no Dirichlet M/F face zeroes
+    unsigned keep[PM];
+#pragma unroll
+    for (int i = 0; i < PM; i++) {
+        const int m = m0 + ty * PM + i;
+        unsigned k = 0;
+        const bool zRow = a.fuse_bc && (((a.bc[2] == 1) & (m == R)) | ((a.bc[3] == 1) & (m == lastM)));
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int f = fMine + c;
+            const bool z = a.fuse_bc && (((a.bc[4] == 1) & (f == R)) | ((a.bc[5] == 1) & (f == lastF)));
+            if (!zRow && !z)
+                k |= 1u << c;
+        }
+        keep[i] = k;
+    }
+    float *outRow = a.next + g.at(z0, m0 + ty * PM, fMine);
+
+    // the plane loop is unrolled UNR times so that the queue shift turns into
+    // register renaming inside the unrolled body
+#pragma unroll UNR
     for (int j = 0; j < planes; j++) {
         const int s = z0 + j;
         const int lf = j + 2 * R;       // newest plane needed
@@ -379,12 +448,12 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
             for (int i = 0; i < PM; i++) {
                 const float4 v = lds4(slot, srow + i, scol);
 #pragma unroll
-                for (int c = 0; c < 4; c++)
+                for (int h = 0; h < 2; h++)
 #pragma unroll
                     for (int k = 0; k < Q - 1; k++)
-                        qv[i][c][k] = qv[i][c][k + 1];
-                qv[i][0][Q - 1] = v.x; qv[i][1][Q - 1] = v.y;
-                qv[i][2][Q - 1] = v.z; qv[i][3][Q - 1] = v.w;
+                        qv[i][h][k] = qv[i][h][k + 1];
+                qv[i][0][Q - 1] = make_float2(v.x, v.y);
+                qv[i][1][Q - 1] = make_float2(v.z, v.w);
             }
         }
 
@@ -396,7 +465,7 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
         const float *sQ = sC0 + TL::STR_FLOATS;
 
         const float *ctr = slot_ptr(lc);
-        float out[PM][4];
+        float2 out[PM][2];
 
 #pragma unroll
         for (int i = 0; i < PM; i++) {
@@ -407,45 +476,44 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 const float4 v = lds4(ctr, srow + i, scol - RP + 4 * b);
                 w[4 * b + 0] = v.x; w[4 * b + 1] = v.y; w[4 * b + 2] = v.z; w[4 * b + 3] = v.w;
             }
-            Stencil3<float, MATH> acc[4];
-            float fpF[4], fpM[4], fpS[4];       // first derivatives of u (variable density)
+            Stencil3x2<MATH> acc[2];
+            float2 fpF[2], fpM[2], fpS[2];      // first derivatives of u (variable density)
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                acc[c].begin(a, qv[i][c][R]);
-                fpF[c] = fpM[c] = fpS[c] = 0.0f;
+            for (int h = 0; h < 2; h++) {
+                acc[h].begin(a, qv[i][h][R]);
+                fpF[h] = fpM[h] = fpS[h] = make_float2(0.0f, 0.0f);
             }
 #pragma unroll
             for (int ir = 1; ir <= R; ir++) {
                 const float4 up = lds4(ctr, srow + i + ir, scol);
                 const float4 dn = lds4(ctr, srow + i - ir, scol);
-                const float upv[4] = {up.x, up.y, up.z, up.w};
-                const float dnv[4] = {dn.x, dn.y, dn.z, dn.w};
+                const float2 upv[2] = {make_float2(up.x, up.y), make_float2(up.z, up.w)};
+                const float2 dnv[2] = {make_float2(dn.x, dn.y), make_float2(dn.z, dn.w)};
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    acc[c].ring(a, ir, w[RP + c + ir], w[RP + c - ir], upv[c], dnv[c],
-                                qv[i][c][R + ir], qv[i][c][R - ir]);
+                for (int h = 0; h < 2; h++) {
+                    const int c = 2 * h;
+                    const float2 fp = make_float2(w[RP + c + ir], w[RP + c + ir + 1]);
+                    const float2 fm = make_float2(w[RP + c - ir], w[RP + c - ir + 1]);
+                    acc[h].ringF(a, ir, fp, fm);
+                    acc[h].ringM(a, ir, upv[h], dnv[h]);
+                    acc[h].ringS(a, ir, qv[i][h][R + ir], qv[i][h][R - ir]);
                     if (VARDEN) {
-                        fpF[c] = ring_diff<float, MATH>(fpF[c], a.c1[ir], w[RP + c + ir],
-                                                        w[RP + c - ir]);
-                        fpM[c] = ring_diff<float, MATH>(fpM[c], a.c1[ir], upv[c], dnv[c]);
-                        fpS[c] = ring_diff<float, MATH>(fpS[c], a.c1[ir], qv[i][c][R + ir],
-                                                        qv[i][c][R - ir]);
+                        fpF[h] = ring_diff2<MATH>(fpF[h], a.c1[ir], fp, fm);
+                        fpM[h] = ring_diff2<MATH>(fpM[h], a.c1[ir], upv[h], dnv[h]);
+                        fpS[h] = ring_diff2<MATH>(fpS[h], a.c1[ir], qv[i][h][R + ir],
+                                                  qv[i][h][R - ir]);
                     }
                 }
             }
             const int off = ((ty * PM + i) * TX + tx) * 4;
             const float4 pv = *reinterpret_cast<const float4 *>(sPrev + off);
             const float4 cv = *reinterpret_cast<const float4 *>(sC0 + off);
-            float4 qd = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (hasQ)
-                qd = *reinterpret_cast<const float4 *>(sQ + off);
-            const float pvv[4] = {pv.x, pv.y, pv.z, pv.w};
-            const float c0a[4] = {cv.x, cv.y, cv.z, cv.w};
-            const float qa[4] = {qd.x, qd.y, qd.z, qd.w};
-            float lap[4];
+            const float2 pvv[2] = {make_float2(pv.x, pv.y), make_float2(pv.z, pv.w)};
+            const float2 c0a[2] = {make_float2(cv.x, cv.y), make_float2(cv.z, cv.w)};
+            float2 lap[2];
 #pragma unroll
-            for (int c = 0; c < 4; c++)
-                lap[c] = acc[c].laplacian(a);
+            for (int h = 0; h < 2; h++)
+                lap[h] = acc[h].laplacian(a);
             if (VARDEN) {
                 float4 rv = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
                 if (MATH == MATH_STRICT)
@@ -453,61 +521,80 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 const float4 gF = *reinterpret_cast<const float4 *>(sPrev + 4 * TL::STR_FLOATS + off);
                 const float4 gM = *reinterpret_cast<const float4 *>(sPrev + 5 * TL::STR_FLOATS + off);
                 const float4 gS = *reinterpret_cast<const float4 *>(sPrev + 6 * TL::STR_FLOATS + off);
-                const float rva[4] = {rv.x, rv.y, rv.z, rv.w};
-                const float gFa[4] = {gF.x, gF.y, gF.z, gF.w};
-                const float gMa[4] = {gM.x, gM.y, gM.z, gM.w};
-                const float gSa[4] = {gS.x, gS.y, gS.z, gS.w};
+                const float2 rva[2] = {make_float2(rv.x, rv.y), make_float2(rv.z, rv.w)};
+                const float2 gFa[2] = {make_float2(gF.x, gF.y), make_float2(gF.z, gF.w)};
+                const float2 gMa[2] = {make_float2(gM.x, gM.y), make_float2(gM.z, gM.w)};
+                const float2 gSa[2] = {make_float2(gS.x, gS.y), make_float2(gS.z, gS.w)};
 #pragma unroll
-                for (int c = 0; c < 4; c++)
-                    lap[c] = (MATH == MATH_STRICT)
-                                 ? density_term<float, 3>(lap[c], fpS[c], gSa[c], fpM[c], gMa[c],
-                                                          fpF[c], gFa[c], a.four_h2, rva[c])
-                                 : fast_density_term<float, 3>(lap[c], fpS[c], gSa[c], fpM[c],
-                                                               gMa[c], fpF[c], gFa[c]);
+                for (int h = 0; h < 2; h++) {
+                    if (MATH == MATH_STRICT) {
+                        lap[h].x = density_term<float, 3>(lap[h].x, fpS[h].x, gSa[h].x, fpM[h].x,
+                                                          gMa[h].x, fpF[h].x, gFa[h].x, a.four_h2,
+                                                          rva[h].x);
+                        lap[h].y = density_term<float, 3>(lap[h].y, fpS[h].y, gSa[h].y, fpM[h].y,
+                                                          gMa[h].y, fpF[h].y, gFa[h].y, a.four_h2,
+                                                          rva[h].y);
+                    } else {
+                        lap[h] = fast_density_term2(lap[h], fpS[h], gSa[h], fpM[h], gMa[h], fpF[h],
+                                                    gFa[h]);
+                    }
+                }
             }
+            if (hasQ) {
+                // absorbing layer inside this tile and plane (warp-uniform)
+                const float4 qd = *reinterpret_cast<const float4 *>(sQ + off);
+                const float2 qa[2] = {make_float2(qd.x, qd.y), make_float2(qd.z, qd.w)};
 #pragma unroll
-            for (int c = 0; c < 4; c++)
-                out[i][c] = update_point<float, MATH>(lap[c], qv[i][c][R], pvv[c], c0a[c], qa[c]);
+                for (int h = 0; h < 2; h++)
+                    out[i][h] = update_pair<MATH, true>(lap[h], qv[i][h][R], pvv[h], c0a[h], qa[h]);
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    out[i][h] = update_pair<MATH, false>(lap[h], qv[i][h][R], pvv[h], c0a[h],
+                                                         make_float2(0.0f, 0.0f));
+            }
         }
 
         // this warp is done with the centre plane and the stream stage
         release(&emptyCur[lc % NS]);
         release(&emptyStr[st]);
 
-        float *alt = a.ghost_copy(s);
-        const bool special = edgeTile | (a.fuse_bc & ((s <= 2 * R) | (s >= lastS - R))) |
-                             (alt != nullptr);
-        if (!special) {
+        if (j >= jPlainLo && j < jPlainHi) {
+            if (tileTier == 0) {
 #pragma unroll
-            for (int i = 0; i < PM; i++) {
-                const long long p = g.at(s, m0 + ty * PM + i, fMine);
-                *reinterpret_cast<float4 *>(a.next + p) =
-                    make_float4(out[i][0], out[i][1], out[i][2], out[i][3]);
-            }
-        } else {
+                for (int i = 0; i < PM; i++)
+                    *reinterpret_cast<float4 *>(outRow + i * g.pitch) =
+                        make_float4(out[i][0].x, out[i][0].y, out[i][1].x, out[i][1].y);
+            } else {
 #pragma unroll
-            for (int i = 0; i < PM; i++) {
-                if (!rowValid[i])
-                    continue;
-                if (a.fuse_bc) {
-                    store_row4(a, s, m0 + ty * PM + i, fMine, out[i], nvalid, alt);
-                } else {
-                    const long long p = g.at(s, m0 + ty * PM + i, fMine);
+                for (int i = 0; i < PM; i++) {
+                    if (!rowValid[i])
+                        continue;
+                    float4 o;
+                    o.x = (keep[i] & 1u) ? out[i][0].x : 0.0f;
+                    o.y = (keep[i] & 2u) ? out[i][0].y : 0.0f;
+                    o.z = (keep[i] & 4u) ? out[i][1].x : 0.0f;
+                    o.w = (keep[i] & 8u) ? out[i][1].y : 0.0f;
+                    float *dst = outRow + i * g.pitch;
                     if (nvalid == 4) {
-                        const float4 o = make_float4(out[i][0], out[i][1], out[i][2], out[i][3]);
-                        *reinterpret_cast<float4 *>(a.next + p) = o;
-                        if (alt)
-                            *reinterpret_cast<float4 *>(alt + p) = o;
+                        *reinterpret_cast<float4 *>(dst) = o;
                     } else {
-                        for (int c = 0; c < nvalid; c++) {
-                            a.next[p + c] = out[i][c];
-                            if (alt)
-                                alt[p + c] = out[i][c];
-                        }
+                        if (nvalid > 0) dst[0] = o.x;
+                        if (nvalid > 1) dst[1] = o.y;
+                        if (nvalid > 2) dst[2] = o.z;
                     }
                 }
             }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PM; i++)
+                if (rowValid[i])
+                    store_row_special(a, s, m0 + ty * PM + i, fMine,
+                                      make_float4(out[i][0].x, out[i][0].y, out[i][1].x,
+                                                  out[i][1].y),
+                                      nvalid);
         }
+        outRow += g.planeStride;
     }
 }
 

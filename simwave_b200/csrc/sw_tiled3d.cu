@@ -3,6 +3,11 @@
 #include "sw_launch.h"
 #include "sw_step_tiled3d.cuh"
 
+// planes per trip of the unrolled plane loop
+#ifndef SW_UNROLL
+#define SW_UNROLL 3
+#endif
+
 namespace sw {
 
 template <int R, int PM, int TX, int TY, int PF, int PS, int MINB, bool VARDEN>
@@ -13,8 +18,9 @@ static void launch_cfg(int math, const StepArgs<float> &a, const StepMaps &maps,
     const Grid &g = a.g;
     dim3 grid((g.nF - 2 * R + TL::BY - 1) / TL::BY, (g.nM - 2 * R + TL::BX - 1) / TL::BX,
               (g.nS - 2 * R + zChunk - 1) / zChunk);
-    auto kStrict = step3d_tiled_kernel<R, PM, TX, TY, PF, PS, MATH_STRICT, MINB, VARDEN>;
-    auto kFast = step3d_tiled_kernel<R, PM, TX, TY, PF, PS, MATH_FAST, MINB, VARDEN>;
+    constexpr int UNR = SW_UNROLL;
+    auto kStrict = step3d_tiled_kernel<R, PM, TX, TY, PF, PS, MATH_STRICT, MINB, VARDEN, UNR>;
+    auto kFast = step3d_tiled_kernel<R, PM, TX, TY, PF, PS, MATH_FAST, MINB, VARDEN, UNR>;
     auto k = (math == MATH_STRICT) ? kStrict : kFast;
     // the shared-memory opt-in is per device: one bit per ordinal
     static unsigned long long configured[2] = {0, 0};

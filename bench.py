@@ -65,7 +65,7 @@ def parse():
                     help="skip the slab-decomposition leg")
     ap.add_argument("--slab-only", action="store_true",
                     help="run only the slab-decomposition leg and print it")
-    ap.add_argument("--slab-planes", type=int, default=128,
+    ap.add_argument("--slab-planes", type=int, default=512,
                     help="owned z-planes per GPU in the slab leg")
     ap.add_argument("--slab-n", type=int, default=1040)
     ap.add_argument("--slab-timesteps", type=int, default=60)

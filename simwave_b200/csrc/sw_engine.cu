@@ -68,6 +68,7 @@ Options Options::from_env()
     o.simple = env_is("SIMWAVE_CUDA_KERNEL", "simple");
     o.debug = env_is("SIMWAVE_CUDA_DEBUG", "1");
     o.separateBc = env_is("SIMWAVE_CUDA_BC", "separate");
+    o.perStep = env_is("SIMWAVE_CUDA_LOOP", "launch");
     o.device = -1;
     if (const char *d = std::getenv("SIMWAVE_CUDA_DEVICE"))
         o.device = std::atoi(d);
@@ -425,7 +426,7 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-typedef bool (*TiledQueryFn)(int, bool, TiledInfo *);
+typedef bool (*TiledQueryFn)(int, bool, int, TiledInfo *);
 typedef bool (*TiledLaunchFn)(int, bool, int, const StepArgs<float> &, const StepMaps &,
                               const unsigned char *, int, cudaStream_t);
 static const TiledQueryFn kTiledQuery[kMaxRadius + 1] = {
@@ -533,6 +534,7 @@ private:
     void launch_sources(const StepArgs<T> &a, size_t n);
     void launch_receivers(const T *cur, size_t n);
     void launch_boundaries(T *next);
+    bool run_persistent(size_t begin, size_t end);
 
     Options opt_;
     int device_ = 0;
@@ -554,6 +556,8 @@ private:
     PointTables<T> srcTab_, recTab_;
     int srcMode_ = SRC_DISJOINT;
     int srcMaxPoints_ = 1;
+    bool srcInterior_ = false;          // every source window lies among the interior points
+    int srcBox_[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // bounding box of the windows, (S,M,F)
     StepFn stepSimple_ = nullptr;
 
     // tiled 3D kernel (float32, constant density)
@@ -564,6 +568,7 @@ private:
     std::map<std::pair<const void *, bool>, CUtensorMap> maps_;
     const CUtensorMap &field_map(const T *base, bool halo);
     void choose_tiling();
+    DeviceBuffer loopBarrier_;   // grid barrier word of the persistent 2D loop
     DeviceBuffer qflags_;   // [nS][tilesM][tilesF]: damping profile non-zero in the tile?
     DeviceBuffer frF_, frM_, frS_;   // first derivatives of the density (tiled variable density)
 
@@ -810,6 +815,18 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
                 }
         }
         srcMode_ = !overlap ? SRC_DISJOINT : (nsrc_ <= 64 ? SRC_ORDERED : SRC_ATOMIC);
+        const int ext[3] = {g.nS, g.nM, g.nF};
+        srcInterior_ = nsrc_ > 0;
+        for (int ax = 0; ax < 3; ax++) { srcBox_[ax][0] = 1 << 30; srcBox_[ax][1] = -1; }
+        for (size_t i = 0; i < nsrc_; i++)
+            for (int ax = 0; ax < ndim_; ax++) {
+                const int lo = (int)iv[(i * ndim_ + ax) * 2], hi = (int)iv[(i * ndim_ + ax) * 2 + 1];
+                const int axis = ax + 3 - ndim_;
+                srcBox_[axis][0] = std::min(srcBox_[axis][0], lo);
+                srcBox_[axis][1] = std::max(srcBox_[axis][1], hi);
+                if (lo < r || hi > ext[axis] - r - 1)
+                    srcInterior_ = false;
+            }
     }
 
     // ---- kernels ---------------------------------------------------------------
@@ -992,17 +1009,22 @@ void Plan<T>::choose_tiling()
             return;
         const int r = g_.r;
         // default configuration, overridable as SIMWAVE_CUDA_TILE=<cfg>[:<zchunk>]
+        int maxSmem = 0;
+        SW_CUDA(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
+        // default: configuration 0; large-radius variable density prefers the
+        // deeper stream ring of configuration 5 where it fits (FAST layout)
         int cfg = 0;
+        if (varden_ && r > 5 && kTiledQuery[r](5, varden_, opt_.math, &tiledInfo_) &&
+            tiledInfo_.smemBytes <= maxSmem)
+            cfg = 5;
         int zchunk = 0;
         if (const char *e = std::getenv("SIMWAVE_CUDA_TILE")) {
             cfg = std::atoi(e);
             if (const char *c = std::strchr(e, ':'))
                 zchunk = std::atoi(c + 1);
         }
-        if (!kTiledQuery[r](cfg, varden_, &tiledInfo_))
+        if (!kTiledQuery[r](cfg, varden_, opt_.math, &tiledInfo_))
             throw Error("SIMWAVE_CUDA_TILE: no such tile configuration");
-        int maxSmem = 0;
-        SW_CUDA(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
         if (tiledInfo_.smemBytes > maxSmem)
             return;   // plain kernel
         tiledCfg_ = cfg;
@@ -1187,7 +1209,8 @@ void Plan<T>::run(size_t begin, size_t end)
     SW_CUDA(cudaEventRecord(evBegin_, stream_));
     if (recBegin_ == recEnd_) { recBegin_ = begin - 1; recEnd_ = begin - 1; }
 
-    for (size_t n = begin; n <= end; n++) {
+    const bool persistent = run_persistent(begin, end);
+    for (size_t n = begin; n <= end && !persistent; n++) {
         // slot indices, as constant_density/3d/wave.c:113-124
         if (stride_ == 0) {
             prevT_ = (n - 1) % 3; curT_ = n % 3; nextT_ = (n + 1) % 3;
@@ -1261,6 +1284,65 @@ void Plan<T>::run(size_t begin, size_t end)
     SW_CUDA(cudaEventElapsedTime(&ms, evBegin_, evEnd_));
     timing.loop = ms * 1e-3;
     timing.run_wall = wall() - t0;
+}
+
+// 2D, three rotating slots: the whole range in one cooperative launch
+// (sw_loop2d.cuh).  Returns false when the per-step path has to run.
+template <typename T>
+bool Plan<T>::run_persistent(size_t begin, size_t end)
+{
+    if (ndim_ != 2 || stride_ != 0 || opt_.perStep || opt_.debug || begin > end)
+        return false;
+    for (size_t s = 0; s < 3; s++)
+        ensure_live(s);
+    LoopArgs<T> L;
+    std::memset(&L, 0, sizeof(L));
+    L.a = args_;
+    for (size_t s = 0; s < 3; s++)
+        L.slot[s] = live_[s];
+    L.src = srcTab_;
+    L.rec = recTab_;
+    L.wavelet = wavelet_.as<T>();
+    L.waveletCount = (int)waveletCount_;
+    L.srcMode = srcMode_;
+    L.srcMaxPoints = srcMaxPoints_;
+    L.fuseSources = (srcInterior_ && nsrc_ <= 8 && srcMode_ != SRC_ATOMIC) ? 1 : 0;
+    L.srcLoM = srcBox_[AX_M][0]; L.srcHiM = srcBox_[AX_M][1];
+    L.srcLoF = srcBox_[AX_F][0]; L.srcHiF = srcBox_[AX_F][1];
+    L.recOut = recOut_.as<T>();
+    L.begin = (long long)begin;
+    L.end = (long long)end;
+    if (!loopBarrier_.get())
+        loopBarrier_.alloc(128);
+    SW_CUDA(cudaMemsetAsync(loopBarrier_.get(), 0, 128, stream_));
+    L.barrier = loopBarrier_.as<unsigned>();
+    const bool trace = std::getenv("SIMWAVE_CUDA_LOOP2D_TRACE") != nullptr;
+    DeviceBuffer traceBuf;
+    if (trace) {
+        traceBuf.alloc(256 * sizeof(unsigned long long));
+        SW_CUDA(cudaMemsetAsync(traceBuf.get(), 0, traceBuf.bytes(), stream_));
+        L.trace = traceBuf.as<unsigned long long>();
+    }
+    const bool ok = varden_ ? launch_loop2d<T, true>(opt_.math, L, stream_)
+                            : launch_loop2d<T, false>(opt_.math, L, stream_);
+    if (!ok)
+        return false;
+    check_launch("loop2d_persistent_kernel");
+    if (trace) {
+        unsigned long long t[256];
+        SW_CUDA(cudaMemcpyAsync(t, traceBuf.get(), sizeof(t), cudaMemcpyDeviceToHost, stream_));
+        SW_CUDA(cudaStreamSynchronize(stream_));
+        std::fprintf(stderr, "simwave_b200: loop2d phases of CTA 0 (ns: receivers, stencil, "
+                             "sources+barriers | per step):");
+        for (int i = 4 * 20; i + 4 < 4 * 26 && t[i + 4]; i += 4)
+            std::fprintf(stderr, " [%llu %llu %llu]", t[i + 1] - t[i], t[i + 2] - t[i + 1],
+                         t[i + 3] - t[i + 2]);
+        std::fprintf(stderr, "\n");
+    }
+    for (size_t n = begin; n <= end; n++)
+        dirty_[(n + 1) % 3] = true;
+    prevT_ = (end - 1) % 3; curT_ = end % 3; nextT_ = (end + 1) % 3;
+    return true;
 }
 
 template <typename T>

@@ -20,6 +20,7 @@ struct Options {
     bool simple;       // force the plain kernels
     bool debug;        // synchronise + check after every launch
     bool separateBc;   // stand-alone boundary kernels instead of the fused form
+    bool perStep;      // 2D: per-step launches instead of the persistent loop kernel
     int device;        // -1: current
     static Options from_env();
 };

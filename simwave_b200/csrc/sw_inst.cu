@@ -2,6 +2,11 @@
 //   -DSW_T=float|double  -DSW_NDIM=2|3  -DSW_VARDEN=0|1
 #include "sw_launch.h"
 #include "sw_step_simple.cuh"
+#if SW_NDIM == 2
+#include <algorithm>
+
+#include "sw_loop2d.cuh"
+#endif
 
 namespace sw {
 
@@ -34,5 +39,9 @@ void launch_step_simple(int math, const StepArgs<T> &a, cudaStream_t stream)
 
 template void launch_step_simple<SW_T, SW_NDIM, (SW_VARDEN != 0)>(int, const StepArgs<SW_T> &,
                                                                    cudaStream_t);
+
+#if SW_NDIM == 2
+template bool launch_loop2d<SW_T, (SW_VARDEN != 0)>(int, const LoopArgs<SW_T> &, cudaStream_t);
+#endif
 
 }  // namespace sw

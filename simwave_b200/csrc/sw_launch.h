@@ -11,6 +11,25 @@ namespace sw {
 template <typename T, int NDIM, bool VARDEN>
 void launch_step_simple(int math, const StepArgs<T> &a, cudaStream_t stream);
 
+// persistent 2D time loop (sw_loop2d.cuh): the whole range [begin, end] of time
+// steps in one cooperative launch; false = not available, use per-step launches
+template <typename T>
+struct LoopArgs {
+    StepArgs<T> a;            // prev / cur / next are taken from `slot`
+    T *slot[3];               // the three rotating wavefield slots
+    PointTables<T> src, rec;
+    const T *wavelet;
+    int waveletCount, srcMode, srcMaxPoints;
+    int fuseSources;          // sources added by the thread that owns the cell
+    int srcLoM, srcHiM, srcLoF, srcHiF;   // bounding box of all source windows
+    T *recOut;                // [wavelet_size][rec.count]
+    long long begin, end;     // time steps, inclusive
+    unsigned *barrier;        // grid barrier counter, zero at launch
+    unsigned long long *trace;   // phase time stamps of CTA 0 (development aid) or nullptr
+};
+template <typename T, bool VARDEN>
+bool launch_loop2d(int math, const LoopArgs<T> &L, cudaStream_t stream);
+
 // ---- tiled 3D kernel (float32, constant density) ---------------------------
 struct TiledInfo {
     int pm, tx, ty, pf, ps; // points per thread along M, thread columns / rows, prefetch depths
@@ -31,7 +50,7 @@ struct StepMaps {
     CUtensorMap rho, frF, frM, frS;     // variable density only
 };
 #define SW_DECL_TILED(R)                                                              \
-    bool tiled3d_query_r##R(int cfg, bool varden, TiledInfo *info);                   \
+    bool tiled3d_query_r##R(int cfg, bool varden, int math, TiledInfo *info);                   \
     bool tiled3d_launch_r##R(int cfg, bool varden, int math, const StepArgs<float> &a, \
                              const StepMaps &maps, const unsigned char *qflags,       \
                              int zChunk, cudaStream_t stream);

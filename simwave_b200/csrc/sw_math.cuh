@@ -150,12 +150,29 @@ __device__ __forceinline__ T leapfrog(T lap, T u, T prev, T c0, T q)
 
 // FAST-mode update.  `lap` already carries the 1/h^2 factors.
 //   q == 0:  u_next = (2u - prev) + lap*c0
-//   q != 0:  u_next = (2u - (1-q) prev + lap*c0) / (1+q)
+//   q != 0:  u_next = (2u - (1-q) prev + lap*c0) * (1/(1+q))
 // (the same expression as above multiplied out: 2/D u - N/D prev + lap c0/D).
 // 2u - prev is exact in the working precision wherever u and prev are of the
 // same sign and size (the usual case: the field varies slowly from one step
 // to the next), so rounding it separately costs nothing measurable against
 // the reference's double accumulation (measured: tools/parity_report.py).
+// 1/d for d in [1, 2): float32 goes through the hardware reciprocal
+// (rcp.approx, 1 ulp) and one Newton step instead of an IEEE division -- the
+// division's range checks and slow path cost more than the rest of the update
+// inside an absorbing layer.  float64 divides.
+template <typename T>
+__device__ __forceinline__ T fast_reciprocal(T d)
+{
+    return Ops<T>::div(T(1), d);
+}
+template <>
+__device__ __forceinline__ float fast_reciprocal<float>(float d)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return Ops<float>::mul(r, Ops<float>::fma(-d, r, 2.0f));
+}
+
 template <typename T>
 __device__ __forceinline__ T fast_leapfrog(T lap, T u, T prev, T c0, T q)
 {
@@ -163,7 +180,7 @@ __device__ __forceinline__ T fast_leapfrog(T lap, T u, T prev, T c0, T q)
         return Ops<T>::fma(lap, c0, Ops<T>::fma(T(2), u, -prev));
     const T N = Ops<T>::sub(T(1), q);
     const T t = Ops<T>::fma(lap, c0, Ops<T>::fma(-N, prev, Ops<T>::add(u, u)));
-    return Ops<T>::div(t, Ops<T>::add(T(1), q));
+    return Ops<T>::mul(t, fast_reciprocal<T>(Ops<T>::add(T(1), q)));
 }
 
 // One interface for both modes: `lap` is what Stencil<..>::laplacian returns.
@@ -320,12 +337,24 @@ template <int MATH, bool DAMPED>
 __device__ __forceinline__ float2 update_pair(float2 lap, float2 u, float2 prev, float2 c0,
                                               float2 q)
 {
-    if (MATH == MATH_STRICT || DAMPED)
+    if (MATH == MATH_STRICT)
         return make_float2(update_point<float, MATH>(lap.x, u.x, prev.x, c0.x, DAMPED ? q.x : 0.0f),
                            update_point<float, MATH>(lap.y, u.y, prev.y, c0.y, DAMPED ? q.y : 0.0f));
-    // fma(lap, c0, fma(2, u, -prev)), both lanes
-    const float2 t = Pair::fma(Pair::bc(2.0f), u, make_float2(-prev.x, -prev.y));
-    return Pair::fma(lap, c0, t);
+    if (!DAMPED) {
+        // fma(lap, c0, fma(2, u, -prev)), both lanes
+        const float2 t = Pair::fma(Pair::bc(2.0f), u, make_float2(-prev.x, -prev.y));
+        return Pair::fma(lap, c0, t);
+    }
+    // fast_leapfrog's damped form, lane for lane (for q == 0 it reduces to the
+    // undamped expression bit for bit: N == 1, 1/(1+q) == 1)
+    const float2 N = Pair::sub(Pair::bc(1.0f), q);
+    const float2 t = Pair::fma(lap, c0, Pair::fma(make_float2(-N.x, -N.y), prev, Pair::add(u, u)));
+    const float2 D = Pair::add(Pair::bc(1.0f), q);
+    float2 r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(D.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(D.y));
+    r = Pair::mul(r, Pair::fma(make_float2(-D.x, -D.y), r, Pair::bc(2.0f)));
+    return Pair::mul(t, r);
 }
 
 // source increment: dt^2/slowness * kws * wavelet / D           (3d/wave.c:277)

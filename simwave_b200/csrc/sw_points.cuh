@@ -76,7 +76,7 @@ __global__ void rho_gradient_kernel(const __grid_constant__ StepArgs<T> a, T *__
 // flags[(s*tilesM + tm)*tilesF + tf] = 1 where q != 0 somewhere among the
 // interior points of tile (tm,tf) on plane s.  One block per (tile, plane);
 // blockIdx.z counts interior planes.
-__global__ void qflag_kernel(Grid g, const float *__restrict__ q, int tileM, int tileF,
+static __global__ void qflag_kernel(Grid g, const float *__restrict__ q, int tileM, int tileF,
                              unsigned char *__restrict__ flags)
 {
     const int s = g.r + blockIdx.z;
@@ -219,11 +219,15 @@ enum SourceMode {
                        // reference's OpenMP build has: unspecified)
 };
 
-// Section 2 of the reference loop (3d/wave.c:208-295, 2d/wave.c:199-271)
+// Section 2 of the reference loop (3d/wave.c:208-295, 2d/wave.c:199-271).
+// Work is spread like a 2D launch: (bx, gx) = block index / count along the
+// cells of a window, (by, gy) along the sources.
 template <typename T, int NDIM>
-__global__ void source_kernel(const __grid_constant__ StepArgs<T> a, PointTables<T> tab,
-                              const T *__restrict__ wavelet, int waveletCount, long long step,
-                              int mode)
+__device__ __forceinline__ void source_apply(const StepArgs<T> &a, T *next,
+                                             const PointTables<T> &tab,
+                                             const T *__restrict__ wavelet, int waveletCount,
+                                             long long step, int mode, int bx, int gx, int by,
+                                             int gy)
 {
     auto wavelet_of = [&](int sid) {
         long long wo = step - 1;
@@ -232,15 +236,14 @@ __global__ void source_kernel(const __grid_constant__ StepArgs<T> a, PointTables
         return wavelet[wo];
     };
 
-    for (int src = blockIdx.y; src < tab.count; src += gridDim.y) {
+    for (int src = by; src < tab.count; src += gy) {
         const Window<T, NDIM> win(tab, src);
         const int total = win.points();
         const T w = wavelet_of(src);
         if (mode != SRC_ORDERED && w == T(0))
             continue;
 
-        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-             idx += gridDim.x * blockDim.x) {
+        for (int idx = bx * blockDim.x + threadIdx.x; idx < total; idx += gx * blockDim.x) {
             const int jf = idx % win.n[2];
             const int im = (idx / win.n[2]) % win.n[1];
             const int is = idx / (win.n[2] * win.n[1]);
@@ -263,17 +266,26 @@ __global__ void source_kernel(const __grid_constant__ StepArgs<T> a, PointTables
                         continue;
                     const T kws =
                         other.weight(s - other.lo[0], m - other.lo[1], f - other.lo[2]);
-                    add_with_boundaries<T, NDIM>(a, a.next, s, m, f,
+                    add_with_boundaries<T, NDIM>(a, next, s, m, f,
                                                  source_term<T>(a.c0[p], a.q[p], kws, wt), false);
                 }
             } else {
                 const T kws = win.weight(is, im, jf);
-                add_with_boundaries<T, NDIM>(a, a.next, s, m, f,
+                add_with_boundaries<T, NDIM>(a, next, s, m, f,
                                              source_term<T>(a.c0[p], a.q[p], kws, w),
                                              mode == SRC_ATOMIC);
             }
         }
     }
+}
+
+template <typename T, int NDIM>
+__global__ void source_kernel(const __grid_constant__ StepArgs<T> a, PointTables<T> tab,
+                              const T *__restrict__ wavelet, int waveletCount, long long step,
+                              int mode)
+{
+    source_apply<T, NDIM>(a, a.next, tab, wavelet, waveletCount, step, mode, blockIdx.x,
+                          gridDim.x, blockIdx.y, gridDim.y);
 }
 
 // ---------------------------------------------------------------------------
@@ -284,13 +296,9 @@ __global__ void source_kernel(const __grid_constant__ StepArgs<T> a, PointTables
 // per add), so the trace is bit-identical to the sequential C loop.
 // ---------------------------------------------------------------------------
 template <typename T, int NDIM>
-__global__ void receiver_kernel(Grid g, const T *__restrict__ cur, PointTables<T> tab,
-                                T *__restrict__ row)
+__device__ __forceinline__ T receiver_sample(const Grid &g, const T *cur,
+                                             const PointTables<T> &tab, int rec, int lane)
 {
-    const int lane = threadIdx.x & 31;
-    const int rec = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (rec >= tab.count)
-        return;
     const Window<T, NDIM> win(tab, rec);
     const int rows = win.n[0] * win.n[1];
     const int nf = win.n[2];     // <= 2*10+1 < 32
@@ -317,6 +325,18 @@ __global__ void receiver_kernel(Grid g, const T *__restrict__ cur, PointTables<T
                     sum = Ops<T>::add(sum, __shfl_sync(0xffffffffu, prod[b], l));
         }
     }
+    return sum;
+}
+
+template <typename T, int NDIM>
+__global__ void receiver_kernel(Grid g, const T *__restrict__ cur, PointTables<T> tab,
+                                T *__restrict__ row)
+{
+    const int lane = threadIdx.x & 31;
+    const int rec = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (rec >= tab.count)
+        return;
+    const T sum = receiver_sample<T, NDIM>(g, cur, tab, rec, lane);
     if (lane == 0)
         row[rec] = sum;
 }
@@ -328,7 +348,8 @@ __global__ void receiver_kernel(Grid g, const T *__restrict__ cur, PointTables<T
 // `axis` is AX_S / AX_M / AX_F; one thread per line.
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void boundary_axis_kernel(Grid g, T *next, int axis, int before, int after)
+__device__ __forceinline__ void boundary_line(const Grid &g, T *next, int axis, int before,
+                                              int after, long long tid)
 {
     const int r = g.r;
     int n[3] = {g.nS, g.nM, g.nF};
@@ -342,7 +363,6 @@ __global__ void boundary_axis_kernel(Grid g, T *next, int axis, int before, int 
     // 2D: only one other axis
     const int nb = (ob >= 0) ? n[ob] - 2 * r : 1;
     const int na = n[oa] - 2 * r;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (long long)na * nb)
         return;
     const int ia = (int)(tid / nb) + r;
@@ -361,6 +381,13 @@ __global__ void boundary_axis_kernel(Grid g, T *next, int axis, int before, int 
     if (after == 2)
         for (int ir = 1; ir <= r; ir++)
             line[(last + ir) * sa] = line[(last - ir) * sa];
+}
+
+template <typename T>
+__global__ void boundary_axis_kernel(Grid g, T *next, int axis, int before, int after)
+{
+    boundary_line<T>(g, next, axis, before, after,
+                     (long long)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 }  // namespace sw

@@ -96,6 +96,110 @@ __device__ __forceinline__ long long dense_shift(const Grid &g, int denseNx, int
     return g.at((int)ss, mm, ff);
 }
 
+// New value of one interior point from its neighbourhood (before sources and
+// boundary conditions): the arithmetic of section 1 of the reference loop
+// (constant_density/3d/wave.c:142-188, variable_density/3d/wave.c:145-214 and
+// the 2D files), written once for every kernel.  `U` / `D` give the wavefield
+// / density at signed offsets along an axis: C() centre, F(k), M(k), S(k), and
+// M1(k) = the neighbour the FIRST derivative along M uses (it differs from M(k)
+// only under the bug-compatible strides of variable_density/3d/wave.c:185-186).
+template <typename T, int NDIM, bool VARDEN, int R, int MATH, class U, class D>
+__device__ __forceinline__ T value_from_neighbours(const StepArgs<T> &a, const U &u, const D &d,
+                                                   T prevv, T c0v, T qv)
+{
+    const T uc = u.C();
+
+    // second derivatives: c[0]*u + sum_ir c[ir]*(u[+ir] + u[-ir]), per axis
+    Stencil<T, NDIM, MATH> acc;
+    acc.begin(a, uc);
+    T fpF = T(0), fpM = T(0), fpS = T(0);
+    T frF = T(0), frM = T(0), frS = T(0);
+
+#pragma unroll
+    for (int ir = 1; ir <= R; ir++) {
+        acc.ring(a, ir, u.F(ir), u.F(-ir), u.M(ir), u.M(-ir), NDIM == 3 ? u.S(ir) : T(0),
+                 NDIM == 3 ? u.S(-ir) : T(0));
+        if (VARDEN) {
+            fpF = ring_diff<T, MATH>(fpF, a.c1[ir], u.F(ir), u.F(-ir));
+            frF = ring_diff<T, MATH>(frF, a.c1[ir], d.F(ir), d.F(-ir));
+            fpM = ring_diff<T, MATH>(fpM, a.c1[ir], u.M1(ir), u.M1(-ir));
+            frM = ring_diff<T, MATH>(frM, a.c1[ir], d.M1(ir), d.M1(-ir));
+            if (NDIM == 3) {
+                fpS = ring_diff<T, MATH>(fpS, a.c1[ir], u.S(ir), u.S(-ir));
+                frS = ring_diff<T, MATH>(frS, a.c1[ir], d.S(ir), d.S(-ir));
+            }
+        }
+    }
+
+    T lap = acc.laplacian(a);
+    if (VARDEN) {
+        if (MATH == MATH_STRICT) {
+            lap = density_term<T, NDIM>(lap, fpS, frS, fpM, frM, fpF, frF, a.four_h2, d.C());
+        } else {
+            const T rho = d.C();
+            lap = fast_density_term<T, NDIM>(
+                lap, fpS, NDIM == 3 ? density_weight<T>(frS, a.inv_four_h2[AX_S], rho) : T(0),
+                fpM, density_weight<T>(frM, a.inv_four_h2[AX_M], rho), fpF,
+                density_weight<T>(frF, a.inv_four_h2[AX_F], rho));
+        }
+    }
+
+    return update_point<T, MATH>(lap, uc, prevv, c0v, qv);
+}
+
+// neighbourhood of (s,m,f) straight from a pitched field in global memory
+template <typename T>
+struct GlobalNeighbours {
+    const T *base;      // element (0,0,0) of the field
+    const T *p;         // element (s,m,f)
+    const Grid *g;
+    int s, m, f, quirk, denseNx, denseNy;
+    __device__ __forceinline__ T C() const { return p[0]; }
+    __device__ __forceinline__ T F(int k) const { return p[k]; }
+    __device__ __forceinline__ T M(int k) const { return p[(long long)k * g->pitch]; }
+    __device__ __forceinline__ T S(int k) const { return p[(long long)k * g->planeStride]; }
+    __device__ __forceinline__ T M1(int k) const
+    {
+        if (quirk)   // the reference steps by k*nx dense elements here
+            return base[dense_shift(*g, denseNx, denseNy, s, m, f, (long long)k * denseNx)];
+        return M(k);
+    }
+};
+
+// New value of interior point (s,m,f) from `cur` / `prev`, operands straight
+// from global memory.
+template <typename T, int NDIM, bool VARDEN, int R, int MATH>
+__device__ __forceinline__ T simple_value(const StepArgs<T> &a, const T *prev, const T *cur,
+                                          int s, int m, int f)
+{
+    const Grid &g = a.g;
+    const long long p = g.at(s, m, f);
+    const int quirk = (NDIM == 3 && VARDEN) ? a.quirk : 0;
+    const GlobalNeighbours<T> u{cur, cur + p, &g, s, m, f, quirk, a.denseNx, a.denseNy};
+    const GlobalNeighbours<T> d{a.rho, VARDEN ? a.rho + p : nullptr, &g, s, m, f, quirk,
+                                a.denseNx, a.denseNy};
+    return value_from_neighbours<T, NDIM, VARDEN, R, MATH>(a, u, d, prev[p], a.c0[p], a.q[p]);
+}
+
+// Stores the value of interior point (s,m,f) into `next`, with the boundary
+// cells that depend on it when the conditions are fused.
+template <typename T, int NDIM>
+__device__ __forceinline__ void simple_store(const StepArgs<T> &a, T *next, int s, int m, int f,
+                                             T val)
+{
+    const Grid &g = a.g;
+    const long long p = g.at(s, m, f);
+    if (a.fuse_bc) {
+        store_with_boundaries<T, NDIM>(a, next, p, s, m, f, val);
+    } else {
+        next[p] = val;
+        if (NDIM == 3) {
+            if (T *alt = a.ghost_copy(s))
+                alt[p] = val;
+        }
+    }
+}
+
 template <typename T, int NDIM, bool VARDEN, int R, int MATH>
 __global__ void __launch_bounds__(256)
 step_simple_kernel(const __grid_constant__ StepArgs<T> a)
@@ -106,70 +210,8 @@ step_simple_kernel(const __grid_constant__ StepArgs<T> a)
     const int s = (NDIM == 3) ? R + blockIdx.z : 0;
     if (f >= g.nF - R || m >= g.nM - R)
         return;
-
-    const long long p = g.at(s, m, f);
-    const T *u = a.cur + p;
-    const T uc = u[0];
-
-    // second derivatives: c[0]*u + sum_ir c[ir]*(u[+ir] + u[-ir]), per axis
-    Stencil<T, NDIM, MATH> acc;
-    acc.begin(a, uc);
-    T fpF = T(0), fpM = T(0), fpS = T(0);
-    T frF = T(0), frM = T(0), frS = T(0);
-    const T *d = VARDEN ? a.rho + p : nullptr;
-
-#pragma unroll
-    for (int ir = 1; ir <= R; ir++) {
-        const long long oM = (long long)ir * g.pitch;
-        const long long oS = (long long)ir * g.planeStride;
-        acc.ring(a, ir, u[ir], u[-ir], u[oM], u[-oM], NDIM == 3 ? u[oS] : T(0),
-                 NDIM == 3 ? u[-oS] : T(0));
-        if (VARDEN) {
-            fpF = ring_diff<T, MATH>(fpF, a.c1[ir], u[ir], u[-ir]);
-            frF = ring_diff<T, MATH>(frF, a.c1[ir], d[ir], d[-ir]);
-            if (NDIM == 3 && a.quirk) {
-                // reference steps by ir*nx dense elements here
-                const long long hi = dense_shift(g, a.denseNx, a.denseNy, s, m, f,
-                                                 (long long)ir * a.denseNx);
-                const long long lo = dense_shift(g, a.denseNx, a.denseNy, s, m, f,
-                                                 -(long long)ir * a.denseNx);
-                fpM = ring_diff<T, MATH>(fpM, a.c1[ir], a.cur[hi], a.cur[lo]);
-                frM = ring_diff<T, MATH>(frM, a.c1[ir], a.rho[hi], a.rho[lo]);
-            } else {
-                fpM = ring_diff<T, MATH>(fpM, a.c1[ir], u[oM], u[-oM]);
-                frM = ring_diff<T, MATH>(frM, a.c1[ir], d[oM], d[-oM]);
-            }
-            if (NDIM == 3) {
-                fpS = ring_diff<T, MATH>(fpS, a.c1[ir], u[oS], u[-oS]);
-                frS = ring_diff<T, MATH>(frS, a.c1[ir], d[oS], d[-oS]);
-            }
-        }
-    }
-
-    T lap = acc.laplacian(a);
-    if (VARDEN) {
-        if (MATH == MATH_STRICT) {
-            lap = density_term<T, NDIM>(lap, fpS, frS, fpM, frM, fpF, frF, a.four_h2, d[0]);
-        } else {
-            const T rho = d[0];
-            lap = fast_density_term<T, NDIM>(
-                lap, fpS, NDIM == 3 ? density_weight<T>(frS, a.inv_four_h2[AX_S], rho) : T(0),
-                fpM, density_weight<T>(frM, a.inv_four_h2[AX_M], rho), fpF,
-                density_weight<T>(frF, a.inv_four_h2[AX_F], rho));
-        }
-    }
-
-    const T val = update_point<T, MATH>(lap, uc, a.prev[p], a.c0[p], a.q[p]);
-
-    if (a.fuse_bc) {
-        store_with_boundaries<T, NDIM>(a, a.next, p, s, m, f, val);
-    } else {
-        a.next[p] = val;
-        if (NDIM == 3) {
-            if (T *alt = a.ghost_copy(s))
-                alt[p] = val;
-        }
-    }
+    simple_store<T, NDIM>(a, a.next, s, m, f,
+                          simple_value<T, NDIM, VARDEN, R, MATH>(a, a.prev, a.cur, s, m, f));
 }
 
 }  // namespace sw

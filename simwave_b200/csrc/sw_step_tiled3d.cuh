@@ -92,9 +92,12 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 }
 
 // ---- tile geometry -------------------------------------------------------------
-template <int R, int PM, int TX, int TY, int PF, int PS, bool VARDEN = false>
+template <int R, int PM, int TX, int TY, int PF, int PS, bool VARDEN = false, bool RHO = VARDEN>
 struct Tile3D {
-    static constexpr int NSTR = VARDEN ? 7 : 3;      // prev | c0 | q [| rho | frF | frM | frS]
+    // stream tiles of one stage: prev | c0 | q [| frF | frM | frS [| rho]]
+    // (rho itself is streamed only in STRICT mode: FAST folds 1/rho into the
+    // derivatives)
+    static constexpr int NSTR = VARDEN ? (RHO ? 7 : 6) : 3;
     static constexpr int RP = (R + 3) / 4 * 4;       // F halo rounded to a float4
     static constexpr int BX = TY * PM;               // rows (M) per tile
     static constexpr int BY = TX * 4;                // columns (F) per tile
@@ -243,7 +246,7 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                     const __grid_constant__ StepMaps maps,
                     const unsigned char *__restrict__ qflags, int zChunk)
 {
-    using TL = Tile3D<R, PM, TX, TY, PF, PS, VARDEN>;
+    using TL = Tile3D<R, PM, TX, TY, PF, PS, VARDEN, VARDEN && MATH == MATH_STRICT>;
     constexpr int RP = TL::RP, BYH = TL::BYH, NS = TL::NS, NT = TL::NT;
     constexpr int Q = 2 * R + 1;
     constexpr int NCW = TL::CONSUMERS / 32;
@@ -307,13 +310,13 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
             tma_load_3d(dst + TL::STR_FLOATS, &maps.c0, &fullStr[st], g.lpad + f0, m0, z0 + j);
             if (VARDEN) {
                 if (MATH == MATH_STRICT)    // fast math folds 1/rho into the derivatives
-                    tma_load_3d(dst + 3 * TL::STR_FLOATS, &maps.rho, &fullStr[st], g.lpad + f0,
+                    tma_load_3d(dst + 6 * TL::STR_FLOATS, &maps.rho, &fullStr[st], g.lpad + f0,
                                 m0, z0 + j);
-                tma_load_3d(dst + 4 * TL::STR_FLOATS, &maps.frF, &fullStr[st], g.lpad + f0, m0,
+                tma_load_3d(dst + 3 * TL::STR_FLOATS, &maps.frF, &fullStr[st], g.lpad + f0, m0,
                             z0 + j);
-                tma_load_3d(dst + 5 * TL::STR_FLOATS, &maps.frM, &fullStr[st], g.lpad + f0, m0,
+                tma_load_3d(dst + 4 * TL::STR_FLOATS, &maps.frM, &fullStr[st], g.lpad + f0, m0,
                             z0 + j);
-                tma_load_3d(dst + 6 * TL::STR_FLOATS, &maps.frS, &fullStr[st], g.lpad + f0, m0,
+                tma_load_3d(dst + 5 * TL::STR_FLOATS, &maps.frS, &fullStr[st], g.lpad + f0, m0,
                             z0 + j);
             }
             if (hasQ)
@@ -517,10 +520,10 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
             if (VARDEN) {
                 float4 rv = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
                 if (MATH == MATH_STRICT)
-                    rv = *reinterpret_cast<const float4 *>(sPrev + 3 * TL::STR_FLOATS + off);
-                const float4 gF = *reinterpret_cast<const float4 *>(sPrev + 4 * TL::STR_FLOATS + off);
-                const float4 gM = *reinterpret_cast<const float4 *>(sPrev + 5 * TL::STR_FLOATS + off);
-                const float4 gS = *reinterpret_cast<const float4 *>(sPrev + 6 * TL::STR_FLOATS + off);
+                    rv = *reinterpret_cast<const float4 *>(sPrev + 6 * TL::STR_FLOATS + off);
+                const float4 gF = *reinterpret_cast<const float4 *>(sPrev + 3 * TL::STR_FLOATS + off);
+                const float4 gM = *reinterpret_cast<const float4 *>(sPrev + 4 * TL::STR_FLOATS + off);
+                const float4 gS = *reinterpret_cast<const float4 *>(sPrev + 5 * TL::STR_FLOATS + off);
                 const float2 rva[2] = {make_float2(rv.x, rv.y), make_float2(rv.z, rv.w)};
                 const float2 gFa[2] = {make_float2(gF.x, gF.y), make_float2(gF.z, gF.w)};
                 const float2 gMa[2] = {make_float2(gM.x, gM.y), make_float2(gM.z, gM.w)};

@@ -14,7 +14,10 @@ template <int R, int PM, int TX, int TY, int PF, int PS, int MINB, bool VARDEN>
 static void launch_cfg(int math, const StepArgs<float> &a, const StepMaps &maps,
                        const unsigned char *qflags, int zChunk, cudaStream_t stream)
 {
-    using TL = Tile3D<R, PM, TX, TY, PF, PS, VARDEN>;
+    using TLS = Tile3D<R, PM, TX, TY, PF, PS, VARDEN, VARDEN>;      // STRICT layout
+    using TLF = Tile3D<R, PM, TX, TY, PF, PS, VARDEN, false>;       // FAST layout
+    using TL = TLS;
+    const int smemBytes = (math == MATH_STRICT) ? TLS::SMEM_BYTES : TLF::SMEM_BYTES;
     const Grid &g = a.g;
     dim3 grid((g.nF - 2 * R + TL::BY - 1) / TL::BY, (g.nM - 2 * R + TL::BX - 1) / TL::BX,
               (g.nS - 2 * R + zChunk - 1) / zChunk);
@@ -29,17 +32,19 @@ static void launch_cfg(int math, const StepArgs<float> &a, const StepMaps &maps,
     unsigned long long &mask = configured[math == MATH_STRICT];
     if (!(mask >> (dev & 63) & 1ull)) {
         SW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     TL::SMEM_BYTES));
+                                     smemBytes));
         mask |= 1ull << (dev & 63);
     }
-    k<<<grid, TL::THREADS, TL::SMEM_BYTES, stream>>>(a, maps, qflags, zChunk);
+    k<<<grid, TL::THREADS, smemBytes, stream>>>(a, maps, qflags, zChunk);
 }
 
 #define SW_CFG(ID, PM, TX, TY, PF, PS, MINB)                                               \
     case ID:                                                                               \
         if (query) {                                                                       \
             *query = {PM, TX, TY, PF, PS, MINB,                                            \
-                      Tile3D<R, PM, TX, TY, PF, PS, VARDEN>::SMEM_BYTES};                  \
+                      (math == MATH_STRICT)                                                \
+                          ? Tile3D<R, PM, TX, TY, PF, PS, VARDEN, VARDEN>::SMEM_BYTES      \
+                          : Tile3D<R, PM, TX, TY, PF, PS, VARDEN, false>::SMEM_BYTES};     \
             return true;                                                                   \
         }                                                                                  \
         launch_cfg<R, PM, TX, TY, PF, PS, MINB, VARDEN>(math, a, *maps, qflags, zChunk,    \
@@ -90,6 +95,9 @@ static bool dispatch(int cfg, TiledInfo *query, int math, const StepArgs<float> 
             SW_CFG(1, 1, 16, 14, 2, 2, 1)    // 14 x 64 tile, 7+1 warps
             SW_CFG(2, 1, 16, 16, 1, 2, 1)    // 16 x 64 tile, 8+1 warps
             SW_CFG(3, 1, 32, 7, 1, 2, 1)     // 7 x 128 tile, 7+1 warps
+            SW_CFG(4, 1, 16, 22, 2, 2, 1)    // 22 x 64 tile, deeper u_cur prefetch
+            SW_CFG(5, 1, 16, 22, 1, 3, 1)    // 22 x 64 tile, deeper stream prefetch
+            SW_CFG(6, 1, 16, 26, 1, 2, 1)    // 26 x 64 tile, 13+1 warps
         default: return false;
         }
     }
@@ -102,11 +110,12 @@ static bool dispatch(int cfg, TiledInfo *query, int math, const StepArgs<float> 
 #define SW_CAT(a, b) SW_CAT2(a, b)
 
 namespace sw {
-bool SW_CAT(tiled3d_query_r, SW_RADIUS)(int cfg, bool varden, TiledInfo *info)
+bool SW_CAT(tiled3d_query_r, SW_RADIUS)(int cfg, bool varden, int math, TiledInfo *info)
 {
     StepArgs<float> dummy{};
-    return varden ? dispatch<SW_RADIUS, true>(cfg, info, 0, dummy, nullptr, nullptr, 1, nullptr)
-                  : dispatch<SW_RADIUS, false>(cfg, info, 0, dummy, nullptr, nullptr, 1, nullptr);
+    return varden
+               ? dispatch<SW_RADIUS, true>(cfg, info, math, dummy, nullptr, nullptr, 1, nullptr)
+               : dispatch<SW_RADIUS, false>(cfg, info, math, dummy, nullptr, nullptr, 1, nullptr);
 }
 bool SW_CAT(tiled3d_launch_r, SW_RADIUS)(int cfg, bool varden, int math,
                                          const StepArgs<float> &a, const StepMaps &maps,

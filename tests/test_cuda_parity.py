@@ -395,3 +395,103 @@ def test_tiled_kernel_in_place_between_snapshots(monkeypatch):
                               saving_stride=4, seed=6)
     a, b = run_pair(p)
     assert_identical(a, b)
+
+
+# ---------------------------------------------------------------------------
+# persistent 2D time-loop kernel against the per-step launches
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("math", ["strict", "fast"])
+@pytest.mark.parametrize("shape,order,density,dtype,bc", [
+    ((90, 300), 8, False, np.float32, (2, 1, 1, 1)),
+    ((64, 70), 4, True, np.float32, (2, 2, 2, 2)),
+    ((70, 66), 20, True, np.float64, (0, 1, 2, 1)),
+    ((13, 14), 8, False, np.float32, (2, 2, 2, 1)),      # separate boundary passes
+    ((300, 700), 2, False, np.float64, (1, 0, 0, 2))])
+def test_persistent_2d_loop_matches_per_step_launches(shape, order, density,
+                                                      dtype, bc, math,
+                                                      monkeypatch):
+    """One cooperative launch for the whole time loop (sw_loop2d.cuh) must
+    reproduce the three-kernels-per-step path bit for bit: wavefield slots and
+    traces, many overlapping sources and per-source wavelets included."""
+    small = min(shape) < 20
+    p = problems.make_problem(
+        shape=shape, space_order=order, density=density, dtype=dtype,
+        timesteps=45, bc=bc, seed=order, multi_wavelet=True,
+        nbl=((0, 0), (0, 0)) if small else ((0, 5), (4, 6)),
+        num_sources=1 if small else 5, src_radius=1 if small else 4,
+        num_receivers=3 if small else 40, rec_radius=1 if small else 3)
+    monkeypatch.setenv("SIMWAVE_CUDA_MATH", math)
+    monkeypatch.setenv("SIMWAVE_CUDA_LOOP", "launch")
+    per_step = problems.clone(p)
+    cuda_forward(per_step)
+    launches_per_step = core().simwave_cuda_last_launch_count()
+    monkeypatch.delenv("SIMWAVE_CUDA_LOOP")
+    persistent = problems.clone(p)
+    cuda_forward(persistent)
+    launches_persistent = core().simwave_cuda_last_launch_count()
+    assert np.abs(per_step["u"]).max() > 0
+    assert np.array_equal(per_step["u"], persistent["u"])
+    assert np.array_equal(per_step["receivers"], persistent["receivers"])
+    assert launches_persistent < launches_per_step / 10
+
+
+def test_persistent_2d_loop_timestep_windows():
+    """Two consecutive windows of the loop through the plan API equal one run."""
+    from simwave_b200 import slab
+    p = problems.make_problem(shape=(80, 90), space_order=6, timesteps=31, seed=2)
+    whole = problems.clone(p)
+    cuda_forward(whole)
+    q = problems.clone(p)
+    plan = slab.Plan(q)
+    plan.run(1, 10)
+    plan.run(11, 31)
+    plan.download()
+    plan.destroy()
+    assert np.array_equal(whole["u"], q["u"])
+    assert np.array_equal(whole["receivers"], q["receivers"])
+
+
+# ---------------------------------------------------------------------------
+# host data path: pageable and page-locked callers see the same results
+# ---------------------------------------------------------------------------
+def test_pinned_and_pageable_host_buffers_agree():
+    import torch
+    p = problems.make_problem(shape=(40, 150, 160), space_order=8, timesteps=10,
+                              seed=6, nbl=((0, 4), (3, 3), (3, 3)))
+    rng = np.random.default_rng(5)
+    p["u"][1, 8:20] = 1e-3 * rng.standard_normal(p["u"][1, 8:20].shape)
+    pageable = problems.clone(p)
+    cuda_forward(pageable)
+    pinned = problems.clone(p)
+    keep = []
+    for key in ("u", "velocity", "damp", "receivers"):
+        t = torch.from_numpy(pinned[key]).pin_memory()
+        keep.append(t)
+        pinned[key] = t.numpy()
+    cuda_forward(pinned)
+    core().simwave_cuda_release_cache()
+    assert np.array_equal(pageable["u"], pinned["u"])
+    assert np.array_equal(pageable["receivers"], pinned["receivers"])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("density", [False, True])
+@pytest.mark.parametrize("order", [2, 4, 6, 8, 10, 12, 14, 16, 20])
+def test_persistent_2d_loop_every_radius(order, density, dtype, monkeypatch):
+    """Every strip shape of the persistent 2D kernel (rows per thread depend on
+    radius, precision and density) against the per-step launches, bit for bit,
+    on a grid whose extents are not multiples of the tile."""
+    p = problems.make_problem(
+        shape=(61 + 2 * order, 167 + order), space_order=order, density=density,
+        dtype=dtype, timesteps=9, bc=(2, 1, 1, 2), seed=order + 1,
+        nbl=((0, 4), (3, 5)), num_sources=2, src_radius=2, num_receivers=5,
+        rec_radius=2)
+    monkeypatch.setenv("SIMWAVE_CUDA_LOOP", "launch")
+    per_step = problems.clone(p)
+    cuda_forward(per_step)
+    monkeypatch.delenv("SIMWAVE_CUDA_LOOP")
+    persistent = problems.clone(p)
+    cuda_forward(persistent)
+    assert np.abs(per_step["u"]).max() > 0
+    assert np.array_equal(per_step["u"], persistent["u"])
+    assert np.array_equal(per_step["receivers"], persistent["receivers"])

@@ -237,18 +237,7 @@ def slab_3d(rank=0, world=1, planes_per_gpu=128, n=1040, space_order=16,
     def phys(count, before, after):
         idx = np.arange(count, dtype=np.float64) - (before + r)
         return np.clip(idx, 0, count - 2 * r - before - after - 1)
-    zg = phys(nz, *nbl[0])[a:b, None, None]
-    xg = phys(n, *nbl[1])[None, :, None]
-    yg = phys(n, *nbl[2])[None, None, :]
-    bumps = (np.sin(zg / 37.0 + 0.3) * np.cos(xg / 53.0) +
-             np.sin(yg / 41.0 + 1.1) * np.cos(zg / 61.0 + xg / 97.0))
-    depth = zg / max(1.0, float(nz - 2 * r - nbl[0][1] - 1))
-    vel = (vmin + (vmax - vmin) * np.clip(0.15 + 0.6 * depth + 0.12 * bumps, 0, 1)
-           ).astype(dtype)
-    rho = None
-    if density:
-        rho = (1000.0 + 1500.0 * np.clip(0.2 + 0.5 * depth + 0.15 * np.cos(
-            xg / 45.0 + yg / 58.0 + zg / 71.0), 0, 1)).astype(dtype)
+    zfull, xfull, yfull = phys(nz, *nbl[0]), phys(n, *nbl[1]), phys(n, *nbl[2])
 
     # damping mask: what np.pad(linear_ramp, end_values=nbl) builds axis by
     # axis (SpaceModel.damping_mask), in closed form
@@ -261,15 +250,70 @@ def slab_3d(rank=0, world=1, planes_per_gpu=128, n=1040, space_order=16,
         d[:r] = -1
         d[count - r:] = -1                       # halo: no damping
         return d
-    dz = layer_depth(nz, *nbl[0])[a:b, None, None]
-    dx = layer_depth(n, *nbl[1])[None, :, None]
-    dy = layer_depth(n, *nbl[2])[None, None, :]
-    m = np.maximum(dz, 0.0) + 0 * dx + 0 * dy
+    dzfull, dxfull, dyfull = (layer_depth(nz, *nbl[0]), layer_depth(n, *nbl[1]),
+                              layer_depth(n, *nbl[2]))
     nx_l, ny_l = float(nbl[1][0]), float(nbl[2][0])
-    m = m + (nx_l - m) * np.maximum(dx, 0.0) / nx_l
-    m = m + (ny_l - m) * np.maximum(dy, 0.0) / ny_l
-    m = np.where((dz < 0) | (dx < 0) | (dy < 0), 0.0, m)
-    damp = (0.001 * m ** 3).astype(dtype)
+    zscale = max(1.0, float(nz - 2 * r - nbl[0][1] - 1))
+
+    # The fields are closed-form functions of the indices, evaluated in float64
+    # a block of planes at a time -- on the GPU when there is one (a 1040^3
+    # slab is 1.1e9 points per field), with NumPy otherwise; same expressions.
+    try:
+        import torch
+        xp = torch if torch.cuda.is_available() else None
+    except ImportError:
+        xp = None
+
+    def block(z0, z1):
+        if xp is not None:
+            dev = "cuda"
+            t = lambda v: torch.as_tensor(v, dtype=torch.float64, device=dev)  # noqa: E731
+            sin, cos, clip, where, maximum = (torch.sin, torch.cos, torch.clamp,
+                                              torch.where, torch.clamp_min)
+        else:
+            t = lambda v: np.asarray(v, dtype=np.float64)                      # noqa: E731
+            sin, cos, clip, where = np.sin, np.cos, np.clip, np.where
+            maximum = np.maximum
+        zg = t(zfull[z0:z1])[:, None, None]
+        xg = t(xfull)[None, :, None]
+        yg = t(yfull)[None, None, :]
+        bumps = (sin(zg / 37.0 + 0.3) * cos(xg / 53.0) +
+                 sin(yg / 41.0 + 1.1) * cos(zg / 61.0 + xg / 97.0))
+        depth = zg / zscale
+        vel = vmin + (vmax - vmin) * clip(0.15 + 0.6 * depth + 0.12 * bumps, 0, 1)
+        rho = None
+        if density:
+            rho = 1000.0 + 1500.0 * clip(0.2 + 0.5 * depth + 0.15 * cos(
+                xg / 45.0 + yg / 58.0 + zg / 71.0), 0, 1)
+        dz = t(dzfull[z0:z1])[:, None, None]
+        dx = t(dxfull)[None, :, None]
+        dy = t(dyfull)[None, None, :]
+        m = maximum(dz, 0.0) + 0 * dx + 0 * dy
+        m = m + (nx_l - m) * maximum(dx, 0.0) / nx_l
+        m = m + (ny_l - m) * maximum(dy, 0.0) / ny_l
+        m = where((dz < 0) | (dx < 0) | (dy < 0), 0.0 * m, m)
+        damp = 0.001 * m ** 3
+        out = []
+        for f in (vel, rho, damp):
+            if f is None:
+                out.append(None)
+            elif xp is not None:
+                out.append(f.to(torch.float32).cpu().numpy())
+            else:
+                out.append(f.astype(dtype))
+        return out
+
+    vel = np.empty((b - a, n, n), dtype=dtype)
+    rho = np.empty((b - a, n, n), dtype=dtype) if density else None
+    damp = np.empty((b - a, n, n), dtype=dtype)
+    step = 64
+    for z0 in range(a, b, step):
+        z1 = min(b, z0 + step)
+        v_, r_, d_ = block(z0, z1)
+        vel[z0 - a:z1 - a] = v_
+        damp[z0 - a:z1 - a] = d_
+        if density:
+            rho[z0 - a:z1 - a] = r_
 
     hf = [dtype(x) for x in h]
     dt = dtype(fd.calculate_dt(3, space_order, hf, np.array([vmax], dtype=dtype)))

@@ -80,6 +80,18 @@ def measured_peak():
     return 6650.0, "fallback"
 
 
+def profiled_traffic(workload):
+    """Bytes per launch of the dominant kernel from the committed ncu capture
+    (profiles/traffic.json), or None."""
+    path = os.path.join(REPO, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            e = json.load(f).get(workload)
+        return None if e is None else int(e["dram_bytes_read"] + e["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -429,7 +441,9 @@ def run_ours(args, p, rank, world, local_rank):
             "config": workload_config(args, p, T),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak,
+                "traffic": profiled_traffic(p["name"])
+                if os.environ.get("SIMWAVE_CUDA_MATH", "fast") == "fast" else None,
                 "peak_source": peak_kind,
                 "bytes_per_point": bpp,
                 "note": "dominant kernel = stencil step; achieved = %d B x "

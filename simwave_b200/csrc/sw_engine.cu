@@ -1123,6 +1123,7 @@ const CUtensorMap &Plan<T>::field_map(const T *base, bool halo)
     return maps_.emplace(key, m).first->second;
 }
 
+// One time step of the stencil.
 template <typename T>
 void Plan<T>::launch_step(const StepArgs<T> &a)
 {
@@ -1139,10 +1140,13 @@ void Plan<T>::launch_step(const StepArgs<T> &a)
                 maps.frM = field_map(field_base(frM_), false);
                 maps.frS = field_map(field_base(frS_), false);
             }
-            if (!kTiledLaunch[g_.r](tiledCfg_, varden_, opt_.math, a, maps,
-                                    qflags_.as<unsigned char>(), zChunk_, stream_))
-                throw Error("tiled kernel configuration vanished");
-            check_launch("tiled step kernel");
+            auto launch = [&](const StepArgs<T> &args) {
+                if (!kTiledLaunch[g_.r](tiledCfg_, varden_, opt_.math, args, maps,
+                                        qflags_.as<unsigned char>(), zChunk_, stream_))
+                    throw Error("tiled kernel configuration vanished");
+                check_launch("tiled step kernel");
+            };
+            launch(a);
             return;
         }
     }

@@ -204,6 +204,19 @@ loop2d_persistent_kernel(const __grid_constant__ LoopArgs<T> L)
     const long long nwarps = (long long)gridDim.x * warpsPerBlock;
     const long long gwarp = (long long)(gridDim.x - 1 - blockIdx.x) * warpsPerBlock + warp;
 
+    // window of this warp's first receiver: origin, extents, and the lane's
+    // weights along M (row = lane) and along F (column = lane)
+    int recLoM = 0, recLoF = 0, recNM = 0, recNF = 0;
+    T recWM = T(0), recWF = T(0);
+    if (gwarp < L.rec.count) {
+        const Window<T, 2> win(L.rec, (int)gwarp);
+        recLoM = win.lo[1]; recLoF = win.lo[2];
+        recNM = win.n[1]; recNF = win.n[2];
+        if (lane < recNM) recWM = win.w[1][lane];
+        if (lane < recNF) recWF = win.w[2][lane];
+    }
+    const bool recCached = gwarp < L.rec.count && recNM <= 32;
+
     for (long long n = L.begin; n <= L.end; n++) {
         // slot rotation of saving_stride == 0 (2d/wave.c:113-117)
         const T *prev = L.slot[(n - 1) % 3];
@@ -211,10 +224,36 @@ loop2d_persistent_kernel(const __grid_constant__ LoopArgs<T> L)
         T *next = L.slot[(n + 1) % 3];
 
         mark();
-        // receivers: one warp per receiver, trace row n-1
+        // receivers: one warp per receiver, trace row n-1.  The warp's first
+        // receiver has its window and weights in registers (set up before the
+        // loop): per step only the wavefield samples are loaded
         if (L.rec.count) {
             T *row = L.recOut + (n - 1) * L.rec.count;
-            for (long long rec = gwarp; rec < L.rec.count; rec += nwarps) {
+            if (recCached) {
+                T sum = T(0);
+                constexpr int BATCH = 4;
+                for (int r0 = 0; r0 < recNM; r0 += BATCH) {
+                    T prod[BATCH];
+#pragma unroll
+                    for (int b = 0; b < BATCH; b++) {
+                        const int im = r0 + b;
+                        // weight = w_m * w_f, as Window::weight (2d/wave.c:243)
+                        const T kws = Ops<T>::mul(__shfl_sync(0xffffffffu, recWM, im & 31), recWF);
+                        prod[b] = T(0);
+                        if (im < recNM && lane < recNF)
+                            prod[b] = Ops<T>::mul(cur[g.at(0, recLoM + im, recLoF + lane)], kws);
+                    }
+#pragma unroll
+                    for (int b = 0; b < BATCH; b++)
+                        if (r0 + b < recNM)
+                            for (int l = 0; l < recNF; l++)
+                                sum = Ops<T>::add(sum, __shfl_sync(0xffffffffu, prod[b], l));
+                }
+                if (lane == 0)
+                    row[gwarp] = sum;
+            }
+            for (long long rec = recCached ? gwarp + nwarps : gwarp; rec < L.rec.count;
+                 rec += nwarps) {
                 const T sum = receiver_sample<T, 2>(g, cur, L.rec, (int)rec, lane);
                 if (lane == 0)
                     row[rec] = sum;

@@ -396,17 +396,17 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
             release(&emptyCur[l % NS]);
     }
 
-    // Store tiers.  Planes [jPlainLo, jPlainHi) of this CTA lie clear of the
-    // S faces and have no ghost copy; inside that range an interior tile
-    // stores one float4 per row (tier 0), an edge tile without Neumann M/F
-    // faces masks Dirichlet cells and overhanging rows / columns itself
+    // Store tiers.  Planes [jPlainLo, jPlainHi) of this CTA lie clear of the S
+    // faces that carry a boundary condition; inside that range an interior
+    // tile stores one float4 per row (tier 0), an edge tile without Neumann
+    // M/F faces masks Dirichlet cells and overhanging rows / columns itself
     // (tier 1); everything else goes through store_row_special (tier 2).
+    // Planes with a ghost copy on a neighbouring slab repeat the tier 0 / 1
+    // store into the neighbour's memory.
     int jPlainLo, jPlainHi;
     {
-        int sLo = a.fuse_bc ? 2 * R + 1 : 0;               // first plane with s > 2R
-        int sHi = a.fuse_bc ? lastS - R : g.nS;            // first plane with s >= lastS - R
-        if (a.peer[0] != nullptr) sLo = max(sLo, 2 * R);
-        if (a.peer[1] != nullptr) sHi = min(sHi, g.nS - 2 * R);
+        const int sLo = (a.fuse_bc && a.bc[0] != 0) ? 2 * R + 1 : 0;     // first plane with s > 2R
+        const int sHi = (a.fuse_bc && a.bc[1] != 0) ? lastS - R : g.nS;  // first with s >= lastS - R
         jPlainLo = max(sLo - z0, 0);
         jPlainHi = min(sHi - z0, planes);
     }
@@ -436,17 +436,19 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
 
     // the plane loop is unrolled UNR times so that the queue shift turns into
     // register renaming inside the unrolled body
+    // ring positions of the newest plane (j + 2R), the centre plane (j + R) and
+    // the stream stage (j), kept as running counters instead of j % NS etc.
+    int slotF = (2 * R) % NS, parF = ((2 * R) / NS) & 1;
+    int slotC = R % NS;
+    int st = 0, parS = 0;
 #pragma unroll UNR
     for (int j = 0; j < planes; j++) {
         const int s = z0 + j;
-        const int lf = j + 2 * R;       // newest plane needed
-        const int lc = j + R;           // centre plane
-        const int st = j % NT;
 
         // shift the queue and take the newest plane from the ring
-        mbar_wait(&fullCur[lf % NS], (lf / NS) & 1);
+        mbar_wait(&fullCur[slotF], parF);
         {
-            const float *slot = slot_ptr(lf);
+            const float *slot = ring + slotF * TL::SLOT_FLOATS;
 #pragma unroll
             for (int i = 0; i < PM; i++) {
                 const float4 v = lds4(slot, srow + i, scol);
@@ -461,13 +463,13 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
         }
 
         // this plane's streams
-        mbar_wait(&fullStr[st], (j / NT) & 1);
+        mbar_wait(&fullStr[st], parS);
         const bool hasQ = stageHasQ[st] != 0;
         const float *sPrev = streams + st * TL::STAGE_FLOATS;
         const float *sC0 = sPrev + TL::STR_FLOATS;
         const float *sQ = sC0 + TL::STR_FLOATS;
 
-        const float *ctr = slot_ptr(lc);
+        const float *ctr = ring + slotC * TL::SLOT_FLOATS;
         float2 out[PM][2];
 
 #pragma unroll
@@ -479,6 +481,18 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 const float4 v = lds4(ctr, srow + i, scol - RP + 4 * b);
                 w[4 * b + 0] = v.x; w[4 * b + 1] = v.y; w[4 * b + 2] = v.z; w[4 * b + 3] = v.w;
             }
+            // the window as register pairs: we[j] = (w[2j], w[2j+1]) is aligned,
+            // wo[j] = (w[2j+1], w[2j+2]) costs one MOV and serves every ring
+            // that needs it
+            constexpr int NW = (4 + 2 * RP) / 2;
+            float2 we[NW], wo[NW - 1];
+#pragma unroll
+            for (int jw = 0; jw < NW; jw++)
+                we[jw] = make_float2(w[2 * jw], w[2 * jw + 1]);
+#pragma unroll
+            for (int jw = 0; jw < NW - 1; jw++)
+                wo[jw] = make_float2(w[2 * jw + 1], w[2 * jw + 2]);
+            auto wpair = [&](int k) { return (k & 1) ? wo[(k - 1) / 2] : we[k / 2]; };
             Stencil3x2<MATH> acc[2];
             float2 fpF[2], fpM[2], fpS[2];      // first derivatives of u (variable density)
 #pragma unroll
@@ -495,8 +509,8 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int c = 2 * h;
-                    const float2 fp = make_float2(w[RP + c + ir], w[RP + c + ir + 1]);
-                    const float2 fm = make_float2(w[RP + c - ir], w[RP + c - ir + 1]);
+                    const float2 fp = wpair(RP + c + ir);
+                    const float2 fm = wpair(RP + c - ir);
                     acc[h].ringF(a, ir, fp, fm);
                     acc[h].ringM(a, ir, upv[h], dnv[h]);
                     acc[h].ringS(a, ir, qv[i][h][R + ir], qv[i][h][R - ir]);
@@ -559,15 +573,25 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
         }
 
         // this warp is done with the centre plane and the stream stage
-        release(&emptyCur[lc % NS]);
+        release(&emptyCur[slotC]);
         release(&emptyStr[st]);
+        if (++slotF == NS) { slotF = 0; parF ^= 1; }
+        if (++slotC == NS) slotC = 0;
+        if (++st == NT) { st = 0; parS ^= 1; }
 
         if (j >= jPlainLo && j < jPlainHi) {
+            // ghost copy of this plane on a neighbouring slab: same element
+            // index in the neighbour's (pre-shifted) field
+            float *alt = a.ghost_copy(s);
+            float *altRow = alt ? alt + (outRow - a.next) : nullptr;
             if (tileTier == 0) {
 #pragma unroll
-                for (int i = 0; i < PM; i++)
-                    *reinterpret_cast<float4 *>(outRow + i * g.pitch) =
-                        make_float4(out[i][0].x, out[i][0].y, out[i][1].x, out[i][1].y);
+                for (int i = 0; i < PM; i++) {
+                    const float4 o = make_float4(out[i][0].x, out[i][0].y, out[i][1].x, out[i][1].y);
+                    *reinterpret_cast<float4 *>(outRow + i * g.pitch) = o;
+                    if (altRow)
+                        *reinterpret_cast<float4 *>(altRow + i * g.pitch) = o;
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < PM; i++) {
@@ -579,12 +603,20 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                     o.z = (keep[i] & 4u) ? out[i][1].x : 0.0f;
                     o.w = (keep[i] & 8u) ? out[i][1].y : 0.0f;
                     float *dst = outRow + i * g.pitch;
+                    float *dst2 = altRow ? altRow + i * g.pitch : nullptr;
                     if (nvalid == 4) {
                         *reinterpret_cast<float4 *>(dst) = o;
+                        if (dst2)
+                            *reinterpret_cast<float4 *>(dst2) = o;
                     } else {
                         if (nvalid > 0) dst[0] = o.x;
                         if (nvalid > 1) dst[1] = o.y;
                         if (nvalid > 2) dst[2] = o.z;
+                        if (dst2) {
+                            if (nvalid > 0) dst2[0] = o.x;
+                            if (nvalid > 1) dst2[1] = o.y;
+                            if (nvalid > 2) dst2[2] = o.z;
+                        }
                     }
                 }
             }

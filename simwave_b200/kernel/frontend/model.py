@@ -186,8 +186,23 @@ class SpaceModel:
         target_axes = [
             np.linspace(lo, hi, n) for (lo, hi), n in zip(bounds, self.shape)
         ]
-        mesh = np.meshgrid(*target_axes, indexing='ij')
-        return self.dtype(interpolant(tuple(mesh)))
+        # The interpolant is evaluated point by point, so the target grid can
+        # be walked in blocks of leading-axis planes with identical results:
+        # the float64 coordinate meshes of a whole 1024^3 grid (what the
+        # reference builds, and why it runs out of memory there, SURVEY.md
+        # section 7.3) never exist.
+        out = np.empty(self.shape, dtype=self.dtype)
+        plane = int(np.prod(self.shape[1:]))
+        rows = max(1, self._interp_block_bytes // (plane * 8 * (self.dimension + 4)))
+        for lo in range(0, self.shape[0], rows):
+            hi = min(self.shape[0], lo + rows)
+            mesh = np.meshgrid(target_axes[0][lo:hi], *target_axes[1:],
+                               indexing='ij')
+            out[lo:hi] = interpolant(tuple(mesh))
+        return out
+
+    # working-set bound of one interpolation block (float64 meshes + result)
+    _interp_block_bytes = 256 << 20
 
     def config_boundary(self, damping_length=0.0, boundary_condition="none",
                         damping_polynomial_degree=3, damping_alpha=0.001):

@@ -75,3 +75,31 @@ def test_kws_full_axis_matches_window():
                 b1, e1, v1 = kws.axis_window(n, pos, w)
                 assert (b0, e0) == (b1, e1)
                 assert np.array_equal(v0, v1)
+
+
+def test_blockwise_interpolation_is_identical(monkeypatch):
+    """SpaceModel.interpolate walks the target grid in blocks of planes
+    (bounded float64 temporaries); any block size gives the same bits as one
+    evaluation over the whole meshgrid (reference model.py:210-261)."""
+    from scipy.interpolate import RegularGridInterpolator
+    from simwave_b200 import SpaceModel
+    rng = np.random.default_rng(0)
+    for shape, bbox, spacing in (((23, 31), (0, 880, 0, 1200), (7.0, 9.0)),
+                                 ((9, 11, 13), (0, 400, 0, 500, 0, 300), (11., 13., 9.))):
+        vel = (1500 + 3000 * rng.random(shape)).astype(np.float32)
+        monkeypatch.setattr(SpaceModel, "_interp_block_bytes", 1 << 12)
+        small = SpaceModel(bounding_box=bbox, grid_spacing=spacing,
+                           velocity_model=vel, space_order=4)
+        monkeypatch.setattr(SpaceModel, "_interp_block_bytes", 1 << 30)
+        whole = SpaceModel(bounding_box=bbox, grid_spacing=spacing,
+                           velocity_model=vel, space_order=4)
+        assert small.velocity_model.shape == whole.velocity_model.shape
+        assert np.array_equal(small.velocity_model, whole.velocity_model)
+        # and the one-shot evaluation the reference does
+        n = len(shape)
+        bounds = whole._axis_bounds()
+        axes = [np.linspace(lo, hi, shape[i]) for i, (lo, hi) in enumerate(bounds)]
+        tgt = [np.linspace(lo, hi, whole.shape[i]) for i, (lo, hi) in enumerate(bounds)]
+        ref = RegularGridInterpolator(tuple(axes), vel)(
+            tuple(np.meshgrid(*tgt, indexing="ij"))).astype(np.float32)
+        assert np.array_equal(whole.velocity_model, ref)

@@ -35,9 +35,9 @@ def rel_l2(a, b):
 
 CASES = [
     # shape, order, density, steps, bc
-    ((70, 60, 150), 8, False, 40, (2, 1, 2, 1, 0, 2)),
+    ((80, 60, 150), 8, False, 40, (2, 1, 2, 1, 0, 2)),
     ((64, 40, 44), 4, True, 30, (1, 2, 1, 1, 2, 2)),
-    ((90, 50, 70), 16, False, 25, (2, 1, 1, 1, 1, 1)),
+    ((150, 50, 70), 16, False, 25, (2, 1, 1, 1, 1, 1)),     # tall enough for 8 slabs
 ]
 
 

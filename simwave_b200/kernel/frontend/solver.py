@@ -41,36 +41,6 @@ class Solver:
         self._middleware = Middleware(compiler=compiler)
 
     @property
-    def space_model(self):
-        """Space model object."""
-        return self._space_model
-
-    @property
-    def time_model(self):
-        """Time model object."""
-        return self._time_model
-
-    @property
-    def sources(self):
-        """Source object."""
-        return self._sources
-
-    @property
-    def receivers(self):
-        """Receiver object."""
-        return self._receivers
-
-    @property
-    def wavelet(self):
-        """Wavelet object."""
-        return self._wavelet
-
-    @property
-    def compiler(self):
-        """Compiler object."""
-        return self._compiler
-
-    @property
     def snapshot_indexes(self):
         """Time indexes of the wavefields that are kept
         (reference solver.py:68-83)."""
@@ -100,6 +70,20 @@ class Solver:
         shape = (self.num_snapshots + 2,) + self.space_model.extended_shape
         return np.zeros(shape, dtype=self.space_model.dtype)
 
+    @staticmethod
+    def _table_arguments(prefix, acquisition):
+        """The five kernel arguments that describe the interpolation windows
+        of sources ('src') or receivers ('rec'): interval table, weights,
+        per-point offsets and the two sizes (reference solver.py:143-152)."""
+        points, values, offsets = acquisition.interpolated_points_and_values
+        return {
+            prefix + '_points_interval': points,
+            prefix + '_points_interval_size': len(points),
+            prefix + '_points_values': values,
+            prefix + '_points_values_offset': offsets,
+            prefix + '_points_values_size': len(values),
+        }
+
     def forward(self):
         """
         Run the forward propagator.
@@ -112,48 +96,55 @@ class Solver:
             Shot record.
         """
         space, time = self.space_model, self.time_model
-
-        src_points, src_values, src_offsets = \
-            self.sources.interpolated_points_and_values
-        rec_points, rec_values, rec_offsets = \
-            self.receivers.interpolated_points_and_values
-
         u_full = self.u_full
 
-        u_full, recv = self._middleware.exec(
-            operator='forward',
-            u_full=u_full,
-            velocity_model=space.extended_velocity_model,
-            density_model=space.extended_density_model,
-            damping_mask=space.damping_mask,
-            wavelet=self.wavelet.values,
-            wavelet_size=self.wavelet.timesteps,
-            wavelet_count=self.wavelet.num_sources,
-            second_order_fd_coefficients=space.fd_coefficients(2),
-            first_order_fd_coefficients=space.fd_coefficients(1),
-            boundary_condition=space.boundary_condition,
-            src_points_interval=src_points,
-            src_points_interval_size=len(src_points),
-            src_points_values=src_values,
-            src_points_values_offset=src_offsets,
-            src_points_values_size=len(src_values),
-            rec_points_interval=rec_points,
-            rec_points_interval_size=len(rec_points),
-            rec_points_values=rec_values,
-            rec_points_values_offset=rec_offsets,
-            rec_points_values_size=len(rec_values),
-            shot_record=self.shot_record,
-            num_sources=self.sources.count,
-            num_receivers=self.receivers.count,
-            grid_spacing=space.grid_spacing,
-            saving_stride=time.saving_stride,
-            dt=time.dt,
-            begin_timestep=1,
-            end_timestep=time.timesteps,
-            space_order=space.space_order,
-            num_snapshots=u_full.shape[0]
-        )
+        # keyword names are the ones Middleware.exec unpacks into the ABI
+        # argument list (middleware.py, _keys_in_order)
+        arguments = {
+            'u_full': u_full,
+            'shot_record': self.shot_record,
+            'num_snapshots': u_full.shape[0],
+            # model
+            'velocity_model': space.extended_velocity_model,
+            'density_model': space.extended_density_model,
+            'damping_mask': space.damping_mask,
+            'boundary_condition': space.boundary_condition,
+            'grid_spacing': space.grid_spacing,
+            'space_order': space.space_order,
+            'second_order_fd_coefficients': space.fd_coefficients(2),
+            'first_order_fd_coefficients': space.fd_coefficients(1),
+            # time axis
+            'dt': time.dt,
+            'saving_stride': time.saving_stride,
+            'begin_timestep': 1,
+            'end_timestep': time.timesteps,
+            # acquisition
+            'wavelet': self.wavelet.values,
+            'wavelet_size': self.wavelet.timesteps,
+            'wavelet_count': self.wavelet.num_sources,
+            'num_sources': self.sources.count,
+            'num_receivers': self.receivers.count,
+        }
+        arguments.update(self._table_arguments('src', self.sources))
+        arguments.update(self._table_arguments('rec', self.receivers))
+
+        u_full, recv = self._middleware.exec(operator='forward', **arguments)
 
         u_full = time.remove_time_halo_region(u_full)
         u_full = space.remove_halo_region(u_full)
         return u_full, recv
+
+
+def _read_only(attribute, doc):
+    return property(lambda self: getattr(self, '_' + attribute), doc=doc)
+
+
+# the constructor arguments, readable under the reference's names
+for _name, _doc in (('space_model', 'Space model object.'),
+                    ('time_model', 'Time model object.'),
+                    ('sources', 'Source object.'),
+                    ('receivers', 'Receiver object.'),
+                    ('wavelet', 'Wavelet object.'),
+                    ('compiler', 'Compiler object.')):
+    setattr(Solver, _name, _read_only(_name, _doc))
+del _name, _doc

@@ -1,0 +1,54 @@
+"""
+The synthetic workloads bench.py measures (workloads.py): shapes and metadata
+of the five BASELINE.json configurations at reduced size, and the property the
+weak-scaling slab leg rests on -- every rank builds only its own z-slab, and
+the slabs are windows of ONE global model.
+"""
+import numpy as np
+
+import workloads
+from simwave_b200 import slab
+
+
+def test_slab_workload_ranks_are_windows_of_one_global_model():
+    n, planes, world, order = 112, 24, 3, 16
+    r = order // 2
+    whole = workloads.slab_3d(rank=0, world=1, planes_per_gpu=world * planes,
+                              n=n, space_order=order, timesteps=3)
+    nz = world * planes + 2 * r
+    assert whole["velocity"].shape == (nz, n, n)
+    assert whole["damp"].max() > 0 and whole["damp"][r:-r, 50, 50].min() == 0
+    for rank, (lo, hi) in enumerate(slab.split_planes(nz, r, world)):
+        part = workloads.slab_3d(rank=rank, world=world, planes_per_gpu=planes,
+                                 n=n, space_order=order, timesteps=3)
+        a, b = lo - r, hi + r
+        assert part["global_shape"] == (nz, n, n)
+        assert part["owned_planes"] == hi - lo == planes
+        for key in ("velocity", "density", "damp"):
+            assert np.array_equal(part[key], whole[key][a:b]), (rank, key)
+        assert part["slab_up"] == int(rank > 0)
+        assert part["slab_down"] == int(rank < world - 1)
+        # inner faces carry no boundary condition of their own
+        assert part["bc"][0] == (0 if rank > 0 else whole["bc"][0])
+        assert part["bc"][1] == (0 if rank < world - 1 else whole["bc"][1])
+        assert part["dt"] == whole["dt"]
+
+
+def test_named_configurations_have_the_documented_shapes():
+    c1 = workloads.readme_2d(timesteps=4)
+    assert c1["velocity"].shape == (517, 517) and c1["space_order"] == 4
+    c2 = workloads.marmousi_2d(timesteps=4)
+    assert c2["velocity"].shape == (429, 1849) and c2["space_order"] == 8
+    assert len(c2["rec_offsets"]) - 1 == 1700 and c2["damp"].max() > 0
+    assert workloads.interior_points(c2) == 421 * 1841
+    assert workloads.bytes_per_point(c2) == 20
+    vd = workloads.slab_3d(planes_per_gpu=16, n=100, timesteps=2)
+    assert workloads.bytes_per_point(vd) == 24
+
+
+def test_bench_reads_the_profiled_traffic():
+    import bench
+    t = bench.profiled_traffic("overthrust_3d")
+    pts = 207 * 801 * 801                                 # interior points of C3
+    assert t is not None and 16 * pts < t < 20 * pts      # between compulsory and algorithmic
+    assert bench.profiled_traffic("no_such_workload") is None

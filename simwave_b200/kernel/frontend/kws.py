@@ -86,6 +86,79 @@ def axis_window(num_points, source_point, half_width):
     return begin + lo, end + lo, values
 
 
+def batch_axis_windows(num_points, positions, half_width):
+    """
+    ``axis_window`` for many positions on one axis at once.
+
+    Every position gets the same 2*half_width + 4 candidate indices around it
+    (a superset of what ``axis_window`` evaluates); the window function is
+    applied to the whole (count, candidates) matrix with the same element-wise
+    operations on the same dtypes, so each row holds the same float32 weights
+    as the one-by-one path.  Candidates outside the axis are discarded.
+
+    Returns ``begin``, ``end`` (int64 arrays, inclusive) and a list-free pair
+    ``(values, counts)``: the float32 weights of all windows concatenated in
+    position order, and the number of weights per window.
+    """
+    positions = np.asarray(positions)
+    count = positions.shape[0]
+    first = np.floor(positions.astype(np.float64)).astype(np.int64) - half_width - 1
+    candidates = first[:, None] + np.arange(2 * half_width + 4, dtype=np.int64)[None, :]
+    inside = (candidates >= 0) & (candidates <= num_points - 1)
+    # float32 indices are exact integers, as in the reference's linspace
+    index = candidates.astype(np.float32)
+    kws_values = _windowed_sinc(index, positions[:, None], half_width)
+    valid = inside & ~np.isnan(kws_values)
+    counts = valid.sum(axis=1)
+    if count and counts.min() == 0:
+        raise Exception(
+            "There is no valid point in the source/receiver location"
+        )
+    # valid candidates of a row are contiguous: the window is an interval
+    begin = np.where(valid, candidates, np.iinfo(np.int64).max).min(axis=1)
+    end = np.where(valid, candidates, np.iinfo(np.int64).min).max(axis=1)
+    return begin, end, kws_values[valid].astype(np.float32), counts
+
+
+def get_source_points_batch(grid_shape, locations, half_width):
+    """
+    ``get_source_points`` for an array of locations, shape (count, ndim):
+    the three tables the kernel consumes -- uint64 intervals
+    ``[b_axis1, e_axis1, ..]`` per location, the concatenated float32 weights
+    ``[axis1.., axis2.., ..]`` per location, and the uint64 running offsets of
+    each location's weights (length count + 1).  Bit-identical to calling
+    ``get_source_points`` location by location.
+    """
+    locations = np.asarray(locations)
+    if locations.ndim != 2 or locations.shape[1] != len(grid_shape):
+        raise Exception(
+            "Grid and source/receiver location must have the same dimension."
+        )
+    count, ndim = locations.shape
+    intervals = np.empty((count, 2 * ndim), dtype=np.uint)
+    axis_values, axis_counts = [], []
+    for axis, num_points in enumerate(grid_shape):
+        begin, end, values, counts = batch_axis_windows(
+            num_points, locations[:, axis], half_width)
+        intervals[:, 2 * axis] = begin
+        intervals[:, 2 * axis + 1] = end
+        axis_values.append(values)
+        axis_counts.append(counts)
+
+    per_location = np.sum(axis_counts, axis=0) if count else np.zeros(0, np.int64)
+    offsets = np.zeros(count + 1, dtype=np.uint)
+    offsets[1:] = np.cumsum(per_location)
+    weights = np.empty(int(offsets[-1]), dtype=np.float32)
+    # scatter every axis' weights behind the previous axes' of the same location
+    start = offsets[:-1].astype(np.int64)
+    for values, counts in zip(axis_values, axis_counts):
+        owner = np.repeat(np.arange(count), counts)
+        within = np.arange(values.size) - np.repeat(np.cumsum(counts) - counts, counts)
+        weights[start[owner] + within] = values
+        start = start + counts
+    return intervals.reshape(-1), weights, offsets
+
+
 def get_source_points(grid_shape, source_location, half_width):
     """
     Point interval and weights of one source/receiver over all axes

@@ -112,27 +112,10 @@ class Source:
         ndarray
             uint64 running offsets into the weights, length count + 1.
         """
-        shape = self.space_model.extended_shape
-        intervals = []
-        weights = []
-        offsets = [0]
-
-        for position in self.adjusted_grid_positions:
-            p, v = kws.get_source_points(
-                grid_shape=shape,
-                source_location=position,
-                half_width=self.window_radius
-            )
-            intervals.append(p)
-            weights.append(v)
-            offsets.append(offsets[-1] + v.size)
-
-        dtype = self.space_model.dtype
-        points = (np.concatenate(intervals).astype(np.uint)
-                  if intervals else np.array([], dtype=np.uint))
-        values = (np.concatenate(weights).astype(dtype)
-                  if weights else np.array([], dtype=dtype))
-        return points, values, np.asarray(offsets, dtype=np.uint)
+        points, weights, offsets = kws.get_source_points_batch(
+            self.space_model.extended_shape, self.adjusted_grid_positions,
+            self.window_radius)
+        return points, weights.astype(self.space_model.dtype), offsets
 
 
 # a receiver is positioned and interpolated exactly like a source

@@ -103,3 +103,27 @@ def test_blockwise_interpolation_is_identical(monkeypatch):
         ref = RegularGridInterpolator(tuple(axes), vel)(
             tuple(np.meshgrid(*tgt, indexing="ij"))).astype(np.float32)
         assert np.array_equal(whole.velocity_model, ref)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("half_width", [1, 4, 10])
+def test_batched_tables_equal_one_by_one(half_width, dtype):
+    """The tables of a whole acquisition are built in one vectorised pass
+    (kws.get_source_points_batch); they must equal the position-by-position
+    construction bit for bit, windows clipped at the grid ends included."""
+    from simwave_b200.kernel.frontend import kws
+    rng = np.random.default_rng(half_width)
+    for shape in ((57, 131), (23, 31, 29)):
+        top = np.array(shape) - 1
+        pos = (rng.random((64, len(shape))) * top).astype(dtype)
+        pos[:4] = 0
+        pos[4:8] = top
+        pos[8:12] = np.round(pos[8:12])
+        iv, weights, offsets = kws.get_source_points_batch(shape, pos, half_width)
+        one = [kws.get_source_points(shape, [dtype(x) for x in p], half_width)
+               for p in pos]
+        assert np.array_equal(iv, np.concatenate([a for a, _ in one]))
+        assert np.array_equal(weights, np.concatenate([b for _, b in one]))
+        assert np.array_equal(np.diff(offsets.astype(np.int64)),
+                              [b.size for _, b in one])
+        assert iv.dtype == np.uint and weights.dtype == np.float32

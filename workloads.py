@@ -15,15 +15,9 @@ BC = {"none": 0, "null_dirichlet": 1, "null_neumann": 2}
 
 
 def _tables(shape, positions, radius, dtype):
-    intervals, values, offsets = [], [], [0]
-    for pos in positions:
-        p, v = kws.get_source_points(shape, [dtype(x) for x in pos], radius)
-        intervals.append(p)
-        values.append(v)
-        offsets.append(offsets[-1] + v.size)
-    return (np.concatenate(intervals).astype(np.uint64),
-            np.concatenate(values).astype(dtype),
-            np.asarray(offsets, dtype=np.uint64))
+    iv, values, offsets = kws.get_source_points_batch(
+        shape, np.asarray(positions, dtype=dtype), radius)
+    return iv.astype(np.uint64), values.astype(dtype), offsets.astype(np.uint64)
 
 
 def _damping(inner_shape, nbl, halo, alpha, degree, dtype):

@@ -73,10 +73,18 @@ def parse():
 
 
 def measured_peak():
+    """HBM copy bandwidth of this pool's B200s in GB/s: the driver-written
+    MEASURED_PEAKS.json when present ("measured"), else the profiling recipe's
+    fallback of 6.65 TB/s ("fallback")."""
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
+    try:
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured"
+            peaks = json.load(f)
+        value = float(peaks["hbm_gbs"])
+        if value > 0:
+            return value, "measured"
+    except (OSError, ValueError, KeyError, TypeError):
+        pass
     return 6650.0, "fallback"
 
 
@@ -427,8 +435,13 @@ def run_ours(args, p, rank, world, local_rank):
     # ---- slab decomposition leg (C4-shaped, weak scaling) --------------------
     slab_result = None
     if not args.no_slab:
-        slab_result = run_slab_leg(args, rank, world, dist, barrier,
-                                   max_over_ranks)
+        try:
+            slab_result = run_slab_leg(args, rank, world, dist, barrier,
+                                       max_over_ranks)
+        except Exception as e:      # the extra leg must not sink the bench line
+            if world > 1:
+                raise               # ranks wait on each other: fail together
+            slab_result = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank == 0:
         line = {

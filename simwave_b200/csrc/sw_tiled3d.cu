@@ -98,6 +98,8 @@ static bool dispatch(int cfg, TiledInfo *query, int math, const StepArgs<float> 
             SW_CFG(4, 1, 16, 22, 2, 2, 1)    // 22 x 64 tile, deeper u_cur prefetch
             SW_CFG(5, 1, 16, 22, 1, 3, 1)    // 22 x 64 tile, deeper stream prefetch
             SW_CFG(6, 1, 16, 26, 1, 2, 1)    // 26 x 64 tile, 13+1 warps
+            SW_CFG(7, 1, 16, 20, 2, 3, 1)    // 20 x 64 tile, both rings deeper (FAST layout only)
+            SW_CFG(8, 1, 16, 18, 3, 3, 1)    // 18 x 64 tile, 3 u_cur planes in flight (FAST only)
         default: return false;
         }
     }

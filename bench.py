@@ -69,6 +69,10 @@ def parse():
                     help="owned z-planes per GPU in the slab leg")
     ap.add_argument("--slab-n", type=int, default=1040)
     ap.add_argument("--slab-timesteps", type=int, default=60)
+    ap.add_argument("--shots", type=int, default=0,
+                    help="C5 survey leg (with --workload shot_3d): this many "
+                         "shots over one shared model, dealt round-robin to the "
+                         "ranks, each through the drop-in forward()")
     return ap.parse_args()
 
 
@@ -311,6 +315,54 @@ def run_slab_leg(args, rank, world, dist, barrier, max_over_ranks):
     }
 
 
+def run_survey_leg(args, p, rank, world, barrier, max_over_ranks):
+    """C5: a multi-shot survey.  The model stays on the host once per rank
+    (page-locked); every shot is one drop-in forward() call with its own
+    tables, wavefield and traces; shot s runs on rank s mod world.  No
+    data-path collective.  Returns the "survey" object of the bench line."""
+    import workloads
+    from cuda_abi import cuda_forward
+    T = p["end_timestep"]
+    pts = workloads.interior_points(p)
+    host = dict(p)
+    for key in ("velocity", "damp", "wavelet"):
+        host[key] = pinned_like(host[key])
+    host["u"] = pinned_like(p["u"])
+    host["receivers"] = pinned_like(p["receivers"])
+    mine = list(range(rank, args.shots, world))
+    traces = {}
+
+    def shoot(shot):
+        q = workloads.reshoot(p, shot)
+        for key in ("src_intervals", "src_values", "src_offsets",
+                    "rec_intervals", "rec_values", "rec_offsets"):
+            host[key] = q[key]
+        host["u"][...] = 0
+        host["receivers"][...] = 0
+        cuda_forward(host)
+        traces[shot] = float(np.abs(host["receivers"]).max())
+
+    if mine:
+        shoot(mine[0])                      # warm-up: allocation caches, clocks
+    barrier()
+    t0 = time.perf_counter()
+    for shot in mine:
+        shoot(shot)
+    seconds = time.perf_counter() - t0
+    barrier()
+    total = max_over_ranks(seconds)
+    if rank != 0:
+        return None
+    return {"value": args.shots * pts * T / total / 1e9, "unit": "Gpts/s",
+            "shots": args.shots, "shots_per_second": args.shots / total,
+            "seconds": total, "scaling": "strong",
+            "config": {"workload": "survey of %d shots over %s" % (
+                args.shots, workload_config(args, p, T)["workload"]),
+                "parallelism": "shot s on rank s mod %d, one forward() per "
+                               "shot, model arrays shared on the host" % world},
+            "max_abs_trace_of_first_shot": traces.get(0)}
+
+
 def run_ours(args, p, rank, world, local_rank):
     import torch
     import workloads
@@ -447,6 +499,10 @@ def run_ours(args, p, rank, world, local_rank):
                 raise               # ranks wait on each other: fail together
             slab_result = {"error": "%s: %s" % (type(e).__name__, e)}
 
+    survey = None
+    if args.shots > 0 and p["name"] == "shot_3d":
+        survey = run_survey_leg(args, p, rank, world, barrier, max_over_ranks)
+
     if rank == 0:
         line = {
             "metric": "Gpts/s", "value": value, "unit": "Gpts/s",
@@ -469,6 +525,7 @@ def run_ours(args, p, rank, world, local_rank):
             "cpu_baseline": cpu,
             "e2e": e2e,
             "slab": slab_result,
+            "survey": survey,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "wall_ms_per_step": 1e3 * wall / args.steps,

@@ -52,3 +52,18 @@ def test_bench_reads_the_profiled_traffic():
     pts = 207 * 801 * 801                                 # interior points of C3
     assert t is not None and 16 * pts < t < 20 * pts      # between compulsory and algorithmic
     assert bench.profiled_traffic("no_such_workload") is None
+
+
+def test_survey_shots_share_the_model_and_move_the_acquisition():
+    base = workloads.shot_3d(shot=0, n=48, timesteps=4)
+    for shot in (1, 3):
+        fresh = workloads.shot_3d(shot=shot, n=48, timesteps=4)
+        again = workloads.reshoot(base, shot)
+        for key in ("src_intervals", "src_values", "src_offsets",
+                    "rec_intervals", "rec_values", "rec_offsets"):
+            assert np.array_equal(fresh[key], again[key]), key
+        assert again["velocity"] is base["velocity"] and again["damp"] is base["damp"]
+        assert again["u"] is not base["u"] and not again["u"].any()
+        assert again["shot"] == shot
+    assert not np.array_equal(workloads.reshoot(base, 1)["src_intervals"],
+                              base["src_intervals"])

@@ -207,6 +207,35 @@ def shot_3d(shot=0, n=512, space_order=8, timesteps=300, seed=5):
         name="shot_3d")
 
 
+def reshoot(base, shot):
+    """Problem of another shot of the C5 survey over the SAME model arrays as
+    ``base`` (a ``shot_3d`` problem): only the source / receiver tables move
+    (the shot line sits at x = 80 m * shot + 40 m); ``u`` and ``receivers`` are
+    fresh.  A survey driver keeps one model on the host and calls ``forward``
+    once per shot with these."""
+    dtype = base["velocity"].dtype.type
+    n = base["velocity"].shape[0] - base["space_order"]
+    r = base["space_order"] // 2
+    h = np.array([dtype(v) for v in base["spacing"]], dtype=dtype)
+    origin = np.array([r, r, r], dtype=dtype)        # no damping layers in C5
+    x = 80.0 * shot + 40.0
+
+    def to_grid(coords):
+        return np.asarray(coords, dtype=dtype) / h + origin
+    src = [(20.0, x, (n - 1) * 5.0)]
+    rec = [(20.0, x, 10.0 * i) for i in range(n)]
+    shape = base["velocity"].shape
+    p = dict(base)
+    p["src_intervals"], p["src_values"], p["src_offsets"] = _tables(
+        shape, to_grid(src), 4, dtype)
+    p["rec_intervals"], p["rec_values"], p["rec_offsets"] = _tables(
+        shape, to_grid(rec), 4, dtype)
+    p["u"] = np.zeros_like(base["u"])
+    p["receivers"] = np.zeros_like(base["receivers"])
+    p["shot"] = shot
+    return p
+
+
 def slab_3d(rank=0, world=1, planes_per_gpu=128, n=1040, space_order=16,
             density=True, timesteps=60):
     """C4-shaped slab workload for weak scaling: the extended grid is

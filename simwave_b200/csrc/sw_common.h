@@ -12,6 +12,7 @@
 namespace sw {
 
 constexpr int kMaxRadius = 10;  // space_order <= 20 (simwave model.py:47-50)
+constexpr int kSplitMid = kMaxRadius / 2 + 1;   // index of pair k = 0 in StepArgs::c2odd / c1odd
 
 // Axis naming used throughout: F = fastest (contiguous) axis, M = middle axis,
 // S = slowest axis.  3D grids are (S,M,F) = (z,x,y); 2D grids are (M,F) = (z,x)
@@ -50,6 +51,15 @@ struct StepArgs {
     const T *rho;       // density or nullptr
     T c2[kMaxRadius + 1];   // second-derivative half stencil
     T c1[kMaxRadius + 1];   // first-derivative half stencil
+    // "Split" F-axis order of the FAST 3D float32 kernels (sw_math.cuh,
+    // split_f_sums): coefficient pairs of the odd-offset chains.  Entry
+    // kSplitMid + k serves the aligned pair of wavefield values at offsets
+    // (2k, 2k+1) from an even point: {coefficient of offset 2k-1 (what the
+    // odd point of the pair sees in the first value), coefficient of offset
+    // 2k+1 (what the even point sees in the second)}, zero beyond the radius;
+    // c1odd carries the sign of the offset.
+    alignas(2 * sizeof(T)) T c2odd[2 * (kMaxRadius / 2 + 1) + 1][2];
+    alignas(2 * sizeof(T)) T c1odd[2 * (kMaxRadius / 2 + 1) + 1][2];
     T h2[3];            // squared spacing per axis (S,M,F)
     T inv_h2[3];        // 1/h2, correctly rounded (fast math mode only)
     T inv_h2_lo[3];     // 1/h2 - inv_h2 (fast math mode only)

@@ -69,6 +69,9 @@ Options Options::from_env()
     o.debug = env_is("SIMWAVE_CUDA_DEBUG", "1");
     o.separateBc = env_is("SIMWAVE_CUDA_BC", "separate");
     o.perStep = env_is("SIMWAVE_CUDA_LOOP", "launch");
+    o.prefetch = -1;
+    if (const char *d = std::getenv("SIMWAVE_CUDA_PREFETCH"))
+        o.prefetch = std::atoi(d);
     o.device = -1;
     if (const char *d = std::getenv("SIMWAVE_CUDA_DEVICE"))
         o.device = std::atoi(d);
@@ -702,6 +705,18 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
         a.c2[i] = c2[i];
         a.c1[i] = c1 ? c1[i] : T(0);
     }
+    for (int k = -kSplitMid; k <= kSplitMid; k++) {
+        auto coef = [&](const T *c, int off, bool odd_symmetry) {
+            const int m = off < 0 ? -off : off;
+            if (m > r)
+                return T(0);
+            return (odd_symmetry && off < 0) ? -c[m] : c[m];
+        };
+        a.c2odd[kSplitMid + k][0] = coef(a.c2, 2 * k - 1, false);
+        a.c2odd[kSplitMid + k][1] = coef(a.c2, 2 * k + 1, false);
+        a.c1odd[kSplitMid + k][0] = coef(a.c1, 2 * k - 1, true);
+        a.c1odd[kSplitMid + k][1] = coef(a.c1, 2 * k + 1, true);
+    }
     // spacing per axis in (S,M,F) order; squares rounded in T like the
     // reference's `f_type dzSquared = dz * dz`
     T h[3];
@@ -1012,11 +1027,16 @@ void Plan<T>::choose_tiling()
         int maxSmem = 0;
         SW_CUDA(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
         // default: configuration 0; large-radius variable density prefers the
-        // deeper stream ring of configuration 5 where it fits (FAST layout)
+        // deeper rings of configuration 7 (then 5) where they fit (FAST layout)
         int cfg = 0;
-        if (varden_ && r > 5 && kTiledQuery[r](5, varden_, opt_.math, &tiledInfo_) &&
-            tiledInfo_.smemBytes <= maxSmem)
-            cfg = 5;
+        if (varden_ && r > 5) {
+            for (int c : {7, 5})
+                if (kTiledQuery[r](c, varden_, opt_.math, &tiledInfo_) &&
+                    tiledInfo_.smemBytes <= maxSmem) {
+                    cfg = c;
+                    break;
+                }
+        }
         int zchunk = 0;
         if (const char *e = std::getenv("SIMWAVE_CUDA_TILE")) {
             cfg = std::atoi(e);
@@ -1130,6 +1150,9 @@ void Plan<T>::launch_step(const StepArgs<T> &a)
     if constexpr (std::is_same<T, float>::value) {
         if (useTiled_) {
             StepMaps maps;
+            // two planes ahead: +3 % on C3, +6 % on the so-16 variable-density slab;
+            // beyond ~4 the prefetched tiles start evicting each other from L2
+            maps.prefetch = opt_.prefetch >= 0 ? opt_.prefetch : 2;
             maps.cur = field_map(a.cur, true);
             maps.prev = field_map(a.prev, false);
             maps.c0 = field_map(a.c0, false);

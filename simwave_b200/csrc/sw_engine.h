@@ -20,6 +20,7 @@ struct Options {
     bool simple;       // force the plain kernels
     bool debug;        // synchronise + check after every launch
     bool separateBc;   // stand-alone boundary kernels instead of the fused form
+    int prefetch;      // planes of L2 prefetch ahead of the tiled kernel's ring loads (-1: default)
     bool perStep;      // 2D: per-step launches instead of the persistent loop kernel
     int device;        // -1: current
     static Options from_env();

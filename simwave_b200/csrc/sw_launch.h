@@ -48,6 +48,9 @@ namespace sw {
 struct StepMaps {
     CUtensorMap cur, prev, c0, q;
     CUtensorMap rho, frF, frM, frS;     // variable density only
+    // planes by which the producer warp runs ahead with L2 prefetches of every
+    // input tile (cp.async.bulk.prefetch.tensor; 0 = none, at most 32)
+    int prefetch;
 };
 #define SW_DECL_TILED(R)                                                              \
     bool tiled3d_query_r##R(int cfg, bool varden, int math, TiledInfo *info);                   \

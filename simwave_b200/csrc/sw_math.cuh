@@ -216,6 +216,13 @@ struct Stencil {
         if (NDIM == 3)
             sS = ring_sum<T, MATH>(sS, a.c2[ir], sp, sm);
     }
+    // the same ring without the F axis (see split_f_sums)
+    __device__ __forceinline__ void ring_ms(const StepArgs<T> &a, int ir, T mp, T mm, T sp, T sm)
+    {
+        sM = ring_sum<T, MATH>(sM, a.c2[ir], mp, mm);
+        if (NDIM == 3)
+            sS = ring_sum<T, MATH>(sS, a.c2[ir], sp, sm);
+    }
     __device__ __forceinline__ T laplacian(const StepArgs<T> &a) const
     {
         if (MATH == MATH_STRICT)
@@ -237,6 +244,59 @@ struct Stencil {
 };
 template <typename T, int MATH>
 using Stencil3 = Stencil<T, 3, MATH>;
+
+// ---------------------------------------------------------------------------
+// "Split" order of the F-axis sums (FAST mode, 3D, float32).
+//
+// The tiled kernel works on aligned pairs of F-neighbours (two-wide float32
+// instructions).  A ring c[ir]*(u[+ir] + u[-ir]) with odd ir needs the pair
+// (u[f+ir], u[f+1+ir]), which straddles two aligned pairs and costs register
+// moves (about 60 per thread and plane at radius 8: a fifth of all issue
+// slots).  Instead every value of the F window gets its own FMA: the even
+// offsets accumulate in one chain with the pair in place, the odd offsets in
+// a second chain whose two lanes are exchanged (lane 0 gathers the sum of the
+// ODD point, lane 1 of the even one) with a coefficient PAIR per window pair
+// (StepArgs::c2odd / c1odd); one lane-swapping add joins the chains.  Same
+// number of arithmetic instructions, no moves.  Per point this reads:
+//
+//   E = c[0]*u;  for even offsets o != 0 ascending:  E = fma(c[|o|], u[o], E)
+//   O = 0;       for odd offsets o ascending:        O = fma(c[|o|], u[o], O)
+//   sum = E + O
+//
+// (first derivative: the same with sign(o)*c1[|o|], both chains from 0),
+// independent of the lane a point sits in, so the plain kernel evaluates
+// exactly this and the two kernels stay bit-identical.
+// ---------------------------------------------------------------------------
+template <typename T, int NDIM, int MATH>
+constexpr bool kSplitF = false;
+template <>
+constexpr bool kSplitF<float, 3, MATH_FAST> = true;
+
+template <int R, bool VARDEN, class U>
+__device__ __forceinline__ void split_f_sums(const StepArgs<float> &a, const U &u, float &sF,
+                                             float &fpF)
+{
+    float E = sF, O = 0.0f, dE = 0.0f, dO = 0.0f;
+#pragma unroll
+    for (int o = -R; o <= R; o++) {
+        if (o == 0)
+            continue;
+        const int k = o < 0 ? -o : o;
+        const float w = u.F(o);
+        const float c1 = o < 0 ? -a.c1[k] : a.c1[k];
+        if (k % 2 == 0) {
+            E = fmaf(a.c2[k], w, E);
+            if (VARDEN)
+                dE = fmaf(c1, w, dE);
+        } else {
+            O = fmaf(a.c2[k], w, O);
+            if (VARDEN)
+                dO = fmaf(c1, w, dO);
+        }
+    }
+    sF = __fadd_rn(E, O);
+    fpF = __fadd_rn(dE, dO);
+}
 
 // ---------------------------------------------------------------------------
 // Packed pairs.  sm_100a has two-wide float32 instructions (FADD2 / FMUL2 /

@@ -115,12 +115,21 @@ __device__ __forceinline__ T value_from_neighbours(const StepArgs<T> &a, const U
     T fpF = T(0), fpM = T(0), fpS = T(0);
     T frF = T(0), frM = T(0), frS = T(0);
 
+    // F-axis sums of u in split order where the tiled kernel uses it
+    constexpr bool SPLIT = kSplitF<T, NDIM, MATH>;
+    if constexpr (SPLIT)
+        split_f_sums<R, VARDEN>(a, u, acc.sF, fpF);
+
 #pragma unroll
     for (int ir = 1; ir <= R; ir++) {
-        acc.ring(a, ir, u.F(ir), u.F(-ir), u.M(ir), u.M(-ir), NDIM == 3 ? u.S(ir) : T(0),
-                 NDIM == 3 ? u.S(-ir) : T(0));
+        if constexpr (SPLIT)
+            acc.ring_ms(a, ir, u.M(ir), u.M(-ir), u.S(ir), u.S(-ir));
+        else
+            acc.ring(a, ir, u.F(ir), u.F(-ir), u.M(ir), u.M(-ir), NDIM == 3 ? u.S(ir) : T(0),
+                     NDIM == 3 ? u.S(-ir) : T(0));
         if (VARDEN) {
-            fpF = ring_diff<T, MATH>(fpF, a.c1[ir], u.F(ir), u.F(-ir));
+            if constexpr (!SPLIT)
+                fpF = ring_diff<T, MATH>(fpF, a.c1[ir], u.F(ir), u.F(-ir));
             frF = ring_diff<T, MATH>(frF, a.c1[ir], d.F(ir), d.F(-ir));
             fpM = ring_diff<T, MATH>(fpM, a.c1[ir], u.M1(ir), u.M1(-ir));
             frM = ring_diff<T, MATH>(frM, a.c1[ir], d.M1(ir), d.M1(-ir));

@@ -91,6 +91,15 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         : "memory");
 }
 
+// the same box fetched into L2 only (no shared memory, no barrier): lets the
+// producer run far ahead of the rings without holding any on-chip space
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 // ---- tile geometry -------------------------------------------------------------
 template <int R, int PM, int TX, int TY, int PF, int PS, bool VARDEN = false, bool RHO = VARDEN>
 struct Tile3D {
@@ -298,6 +307,9 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
             tma_load_3d(ring + slot * TL::SLOT_FLOATS, &maps.cur, &fullCur[slot],
                         g.lpad + f0 - RP, m0 - R, z0 - R + l);
         };
+        auto load_stream = [&](float *dst, const CUtensorMap *map, uint64_t *bar, int j) {
+            tma_load_3d(dst, map, bar, g.lpad + f0, m0, z0 + j);
+        };
         auto issue_streams = [&](int j, int hasQ) {
             const int st = j % NT;
             if (j >= NT)
@@ -306,39 +318,74 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
             stageHasQ[st] = hasQ;
             constexpr int kDensityTiles = !VARDEN ? 0 : (MATH == MATH_STRICT ? 4 : 3);
             mbar_expect_tx(&fullStr[st], ((hasQ ? 3 : 2) + kDensityTiles) * TL::STR_BYTES);
-            tma_load_3d(dst, &maps.prev, &fullStr[st], g.lpad + f0, m0, z0 + j);
-            tma_load_3d(dst + TL::STR_FLOATS, &maps.c0, &fullStr[st], g.lpad + f0, m0, z0 + j);
+            load_stream(dst, &maps.prev, &fullStr[st], j);
+            load_stream(dst + TL::STR_FLOATS, &maps.c0, &fullStr[st], j);
             if (VARDEN) {
                 if (MATH == MATH_STRICT)    // fast math folds 1/rho into the derivatives
-                    tma_load_3d(dst + 6 * TL::STR_FLOATS, &maps.rho, &fullStr[st], g.lpad + f0,
-                                m0, z0 + j);
-                tma_load_3d(dst + 3 * TL::STR_FLOATS, &maps.frF, &fullStr[st], g.lpad + f0, m0,
-                            z0 + j);
-                tma_load_3d(dst + 4 * TL::STR_FLOATS, &maps.frM, &fullStr[st], g.lpad + f0, m0,
-                            z0 + j);
-                tma_load_3d(dst + 5 * TL::STR_FLOATS, &maps.frS, &fullStr[st], g.lpad + f0, m0,
-                            z0 + j);
+                    load_stream(dst + 6 * TL::STR_FLOATS, &maps.rho, &fullStr[st], j);
+                load_stream(dst + 3 * TL::STR_FLOATS, &maps.frF, &fullStr[st], j);
+                load_stream(dst + 4 * TL::STR_FLOATS, &maps.frM, &fullStr[st], j);
+                load_stream(dst + 5 * TL::STR_FLOATS, &maps.frS, &fullStr[st], j);
             }
             if (hasQ)
-                tma_load_3d(dst + 2 * TL::STR_FLOATS, &maps.q, &fullStr[st], g.lpad + f0, m0,
-                            z0 + j);
+                load_stream(dst + 2 * TL::STR_FLOATS, &maps.q, &fullStr[st], j);
         };
-        if (lane == 0)
+        // L2 prefetches, `ahead` planes in front of the loads into the rings:
+        // the DRAM latency is paid there, the ring loads then hit L2, so a few
+        // stages of shared memory cover what is left
+        const int ahead = min(max(maps.prefetch, 0), 32);
+        auto prefetch_cur = [&](int l) {
+            tma_prefetch_3d(&maps.cur, g.lpad + f0 - RP, m0 - R, z0 - R + l);
+        };
+        auto prefetch_streams = [&](int j, int hasQ) {
+            tma_prefetch_3d(&maps.prev, g.lpad + f0, m0, z0 + j);
+            tma_prefetch_3d(&maps.c0, g.lpad + f0, m0, z0 + j);
+            if (VARDEN) {
+                if (MATH == MATH_STRICT)
+                    tma_prefetch_3d(&maps.rho, g.lpad + f0, m0, z0 + j);
+                tma_prefetch_3d(&maps.frF, g.lpad + f0, m0, z0 + j);
+                tma_prefetch_3d(&maps.frM, g.lpad + f0, m0, z0 + j);
+                tma_prefetch_3d(&maps.frS, g.lpad + f0, m0, z0 + j);
+            }
+            if (hasQ)
+                tma_prefetch_3d(&maps.q, g.lpad + f0, m0, z0 + j);
+        };
+        // damping flags of 32 planes starting at plane b, one per lane
+        auto flag_mask = [&](int b) -> unsigned {
+            int flag = 0;
+            if (b + lane < planes)
+                flag = myFlags[(long long)(z0 + b + lane) * tilesPerPlane];
+            return __ballot_sync(0xffffffffu, flag != 0);
+        };
+        unsigned long long bits = flag_mask(0);
+        if (lane == 0) {
             for (int l = 0; l < 2 * R; l++)
                 issue_cur(l);
+            if (ahead > 0) {
+                for (int l = 2 * R; l < min(2 * R + ahead, planes + 2 * R); l++)
+                    prefetch_cur(l);
+                for (int j = 0; j < min(ahead, planes); j++)
+                    prefetch_streams(j, (int)((bits >> j) & 1ull));
+            }
+        }
         for (int jb = 0; jb < planes; jb += 32) {
-            // damping flags of the next 32 planes, one per lane
-            int flag = 0;
-            if (jb + lane < planes)
-                flag = myFlags[(long long)(z0 + jb + lane) * tilesPerPlane];
-            const unsigned mask = __ballot_sync(0xffffffffu, flag != 0);
+            // bits: flags of planes jb .. jb+63
+            bits |= (unsigned long long)flag_mask(jb + 32) << 32;
             if (lane == 0) {
                 const int jend = min(jb + 32, planes);
                 for (int j = jb; j < jend; j++) {
-                    issue_streams(j, (mask >> (j - jb)) & 1);
+                    issue_streams(j, (int)((bits >> (j - jb)) & 1ull));
                     issue_cur(j + 2 * R);
+                    if (ahead > 0) {
+                        const int jp = j + ahead;
+                        if (jp < planes) {
+                            prefetch_streams(jp, (int)((bits >> (jp - jb)) & 1ull));
+                            prefetch_cur(jp + 2 * R);
+                        }
+                    }
                 }
             }
+            bits >>= 32;
         }
         return;
     }
@@ -481,18 +528,12 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 const float4 v = lds4(ctr, srow + i, scol - RP + 4 * b);
                 w[4 * b + 0] = v.x; w[4 * b + 1] = v.y; w[4 * b + 2] = v.z; w[4 * b + 3] = v.w;
             }
-            // the window as register pairs: we[j] = (w[2j], w[2j+1]) is aligned,
-            // wo[j] = (w[2j+1], w[2j+2]) costs one MOV and serves every ring
-            // that needs it
+            // the window as aligned register pairs: we[j] = (w[2j], w[2j+1])
             constexpr int NW = (4 + 2 * RP) / 2;
-            float2 we[NW], wo[NW - 1];
+            float2 we[NW];
 #pragma unroll
             for (int jw = 0; jw < NW; jw++)
                 we[jw] = make_float2(w[2 * jw], w[2 * jw + 1]);
-#pragma unroll
-            for (int jw = 0; jw < NW - 1; jw++)
-                wo[jw] = make_float2(w[2 * jw + 1], w[2 * jw + 2]);
-            auto wpair = [&](int k) { return (k & 1) ? wo[(k - 1) / 2] : we[k / 2]; };
             Stencil3x2<MATH> acc[2];
             float2 fpF[2], fpM[2], fpS[2];      // first derivatives of u (variable density)
 #pragma unroll
@@ -500,6 +541,44 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 acc[h].begin(a, qv[i][h][R]);
                 fpF[h] = fpM[h] = fpS[h] = make_float2(0.0f, 0.0f);
             }
+            constexpr bool SPLIT = kSplitF<float, 3, MATH>;
+            if constexpr (SPLIT) {
+                // F axis in split order (sw_math.cuh, split_f_sums): every
+                // aligned window pair feeds an even-offset chain in place and an
+                // odd-offset chain with exchanged lanes; no misaligned pairs
+                constexpr int K = (R + 1) / 2;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    float2 E = acc[h].sF, O = make_float2(0.0f, 0.0f);
+                    float2 dE = make_float2(0.0f, 0.0f), dO = make_float2(0.0f, 0.0f);
+#pragma unroll
+                    for (int k = -K; k <= K; k++) {
+                        const float2 P = we[RP / 2 + h + k];
+                        const int e = k < 0 ? -2 * k : 2 * k;
+                        if (k != 0 && e <= R) {
+                            E = Pair::fma(Pair::bc(a.c2[e]), P, E);
+                            if (VARDEN)
+                                dE = Pair::fma(Pair::bc(k < 0 ? -a.c1[e] : a.c1[e]), P, dE);
+                        }
+                        const int oy = 2 * k - 1 < 0 ? 1 - 2 * k : 2 * k - 1;
+                        const int ox = 2 * k + 1 < 0 ? -1 - 2 * k : 2 * k + 1;
+                        if (oy <= R || ox <= R) {
+                            O = Pair::fma(*reinterpret_cast<const float2 *>(a.c2odd[kSplitMid + k]),
+                                          P, O);
+                            if (VARDEN)
+                                dO = Pair::fma(
+                                    *reinterpret_cast<const float2 *>(a.c1odd[kSplitMid + k]), P, dO);
+                        }
+                    }
+                    acc[h].sF = Pair::add(E, make_float2(O.y, O.x));
+                    fpF[h] = Pair::add(dE, make_float2(dO.y, dO.x));
+                }
+            }
+            // misaligned pairs (odd F offsets) for the ring order of STRICT mode:
+            // wo[j] = (w[2j+1], w[2j+2]) costs register moves
+            auto wpair = [&](int k) {
+                return (k & 1) ? make_float2(w[k], w[k + 1]) : we[k / 2];
+            };
 #pragma unroll
             for (int ir = 1; ir <= R; ir++) {
                 const float4 up = lds4(ctr, srow + i + ir, scol);
@@ -509,13 +588,16 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int c = 2 * h;
-                    const float2 fp = wpair(RP + c + ir);
-                    const float2 fm = wpair(RP + c - ir);
-                    acc[h].ringF(a, ir, fp, fm);
+                    if constexpr (!SPLIT) {
+                        const float2 fp = wpair(RP + c + ir);
+                        const float2 fm = wpair(RP + c - ir);
+                        acc[h].ringF(a, ir, fp, fm);
+                        if (VARDEN)
+                            fpF[h] = ring_diff2<MATH>(fpF[h], a.c1[ir], fp, fm);
+                    }
                     acc[h].ringM(a, ir, upv[h], dnv[h]);
                     acc[h].ringS(a, ir, qv[i][h][R + ir], qv[i][h][R - ir]);
                     if (VARDEN) {
-                        fpF[h] = ring_diff2<MATH>(fpF[h], a.c1[ir], fp, fm);
                         fpM[h] = ring_diff2<MATH>(fpM[h], a.c1[ir], upv[h], dnv[h]);
                         fpS[h] = ring_diff2<MATH>(fpS[h], a.c1[ir], qv[i][h][R + ir],
                                                   qv[i][h][R - ir]);

@@ -10,7 +10,7 @@
 
 namespace sw {
 
-template <int R, int PM, int TX, int TY, int PF, int PS, int MINB, bool VARDEN>
+template <int R, int PM, int TX, int TY, int PF, int PS, int MINB, bool VARDEN, int UNR>
 static void launch_cfg(int math, const StepArgs<float> &a, const StepMaps &maps,
                        const unsigned char *qflags, int zChunk, cudaStream_t stream)
 {
@@ -21,7 +21,6 @@ static void launch_cfg(int math, const StepArgs<float> &a, const StepMaps &maps,
     const Grid &g = a.g;
     dim3 grid((g.nF - 2 * R + TL::BY - 1) / TL::BY, (g.nM - 2 * R + TL::BX - 1) / TL::BX,
               (g.nS - 2 * R + zChunk - 1) / zChunk);
-    constexpr int UNR = SW_UNROLL;
     auto kStrict = step3d_tiled_kernel<R, PM, TX, TY, PF, PS, MATH_STRICT, MINB, VARDEN, UNR>;
     auto kFast = step3d_tiled_kernel<R, PM, TX, TY, PF, PS, MATH_FAST, MINB, VARDEN, UNR>;
     auto k = (math == MATH_STRICT) ? kStrict : kFast;
@@ -38,7 +37,8 @@ static void launch_cfg(int math, const StepArgs<float> &a, const StepMaps &maps,
     k<<<grid, TL::THREADS, smemBytes, stream>>>(a, maps, qflags, zChunk);
 }
 
-#define SW_CFG(ID, PM, TX, TY, PF, PS, MINB)                                               \
+#define SW_CFG(ID, PM, TX, TY, PF, PS, MINB) SW_CFGU(ID, PM, TX, TY, PF, PS, MINB, SW_UNROLL)
+#define SW_CFGU(ID, PM, TX, TY, PF, PS, MINB, UNR)                                         \
     case ID:                                                                               \
         if (query) {                                                                       \
             *query = {PM, TX, TY, PF, PS, MINB,                                            \
@@ -47,8 +47,8 @@ static void launch_cfg(int math, const StepArgs<float> &a, const StepMaps &maps,
                           : Tile3D<R, PM, TX, TY, PF, PS, VARDEN, false>::SMEM_BYTES};     \
             return true;                                                                   \
         }                                                                                  \
-        launch_cfg<R, PM, TX, TY, PF, PS, MINB, VARDEN>(math, a, *maps, qflags, zChunk,    \
-                                                        stream);                           \
+        launch_cfg<R, PM, TX, TY, PF, PS, MINB, VARDEN, UNR>(math, a, *maps, qflags,       \
+                                                             zChunk, stream);              \
         return true;
 
 // PM, TX, TY = points per thread along M, thread columns, thread rows
@@ -100,6 +100,10 @@ static bool dispatch(int cfg, TiledInfo *query, int math, const StepArgs<float> 
             SW_CFG(6, 1, 16, 26, 1, 2, 1)    // 26 x 64 tile, 13+1 warps
             SW_CFG(7, 1, 16, 20, 2, 3, 1)    // 20 x 64 tile, both rings deeper (FAST layout only)
             SW_CFG(8, 1, 16, 18, 3, 3, 1)    // 18 x 64 tile, 3 u_cur planes in flight (FAST only)
+            SW_CFGU(9, 1, 16, 22, 1, 3, 1, 4)    // configuration 5, plane loop unrolled 4x
+            SW_CFGU(10, 1, 16, 22, 1, 3, 1, 6)   // ... 6x (fewer queue moves, longer body)
+            SW_CFGU(11, 1, 16, 26, 1, 2, 1, 6)   // configuration 6, 6x
+            SW_CFGU(12, 1, 16, 22, 1, 3, 1, 2)   // configuration 5, 2x
         default: return false;
         }
     }

@@ -27,11 +27,19 @@ def main():
     ap.add_argument("--math", default="strict,fast")
     ap.add_argument("--space-order", type=int, default=None)
     ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--kw", action="append", default=[],
+                    help="extra integer keyword of the workload builder, key=value")
+    ap.add_argument("--no-simple", action="store_true", help="skip the plain kernel")
+    ap.add_argument("--prefetch", default="",
+                    help="comma list of SIMWAVE_CUDA_PREFETCH distances to cross with the tiles")
     args = ap.parse_args()
 
     kwargs = {"timesteps": args.timesteps}
     if args.space_order:
         kwargs["space_order"] = args.space_order
+    for kv in args.kw:
+        k, v = kv.split("=")
+        kwargs[k] = int(v)
     p = workloads.WORKLOADS[args.workload](**kwargs)
     pts = workloads.interior_points(p)
     bpp = workloads.bytes_per_point(p)
@@ -40,21 +48,28 @@ def main():
 
     from simwave_b200 import slab
 
-    combos = [("simple", "-", m) for m in args.math.split(",")]
+    combos = [] if args.no_simple else [("simple", "-", m, None) for m in args.math.split(",")]
     for m in args.math.split(","):
         for c in args.cfgs.split(","):
             for z in args.zchunks.split(","):
-                combos.append(("tiled", "%s:%s" % (c, z), m))
+                for pf in (args.prefetch.split(",") if args.prefetch else [None]):
+                    combos.append(("tiled", "%s:%s" % (c, z), m, pf))
 
-    for kind, tile, math in combos:
+    for kind, tile, math, extra in combos:
         os.environ["SIMWAVE_CUDA_MATH"] = math
+        tile_label = tile
+        pf = extra
+        if pf is not None:
+            os.environ["SIMWAVE_CUDA_PREFETCH"] = pf
+            tile_label += "/pf%s" % pf
+
         os.environ["SIMWAVE_CUDA_KERNEL"] = "simple" if kind == "simple" else "auto"
         if kind == "tiled":
             os.environ["SIMWAVE_CUDA_TILE"] = tile
         try:
             plan = slab.Plan(p)
         except RuntimeError as e:
-            print("%-7s %-8s %-6s  FAILED: %s" % (kind, tile, math, e))
+            print("%-7s %-14s %-6s  FAILED: %s" % (kind, tile_label, math, e))
             continue
         best = None
         for i in range(args.repeat + 1):
@@ -65,8 +80,8 @@ def main():
         plan.destroy()
         if best:
             g = pts * T / best / 1e9
-            print("%-7s %-8s %-6s  %8.3f ms/step  %8.2f Gpts/s  %5.1f%% of %d GB/s"
-                  % (kind, tile, math, 1e3 * best / T, g, 100 * g * bpp / peak, peak),
+            print("%-7s %-14s %-6s  %8.3f ms/step  %8.2f Gpts/s  %5.1f%% of %d GB/s"
+                  % (kind, tile_label, math, 1e3 * best / T, g, 100 * g * bpp / peak, peak),
                   flush=True)
 
 

@@ -226,6 +226,36 @@ unsigned long long simwave_cuda_last_launch_count(void);
 void simwave_cuda_release_cache(void);
 
 /*
+ * Hints: promises of the caller about the next forward() calls on this thread
+ * (the signature of `forward` is frozen, SURVEY.md section 8b, so they travel
+ * beside it).  Every hint is exact -- the arithmetic and the results that are
+ * copied back do not change -- and off (0) by default; a hint stays in force
+ * until it is set again.  They cover the host <-> device data path of a shot
+ * (SURVEY.md section 8 f2), which the reference's GPU variants pay in full on
+ * every call (constant_density/3d/wave.c:69-80, :623-624; cuda/wave.cu:498-543,
+ * :700-704; solver.py:101-110 allocates a fresh zero `u` per call).
+ *
+ *  SIMWAVE_HINT_WAVEFIELD_IN_ZERO   value != 0: every slot of `u` is zero on
+ *      entry (what simwave's Solver passes): nothing of `u` is read or uploaded.
+ *  SIMWAVE_HINT_WAVEFIELD_OUT       with saving_stride == 0, which of the three
+ *      rotating slots are copied back into `u`: 0 all (the ABI's contract),
+ *      1 only slot end_timestep % 3, the wavefield simwave's Solver returns
+ *      (model.py:639-641), 2 none (receiver traces only).  The other slots of
+ *      `u` are left untouched.  Ignored when saving_stride > 0.
+ *  SIMWAVE_HINT_MODEL_RESIDENT      value = a non-zero token chosen by the
+ *      caller: velocity / damp / density, the grid, dt and space_order are the
+ *      same for every call made under this token, so the device keeps the
+ *      preprocessed model of the last call (per device) and the next one skips
+ *      its upload.  A new token, 0, or simwave_cuda_release_cache() drops it.
+ *
+ * Returns 0, or -1 for an unknown hint / value (see simwave_cuda_last_error).
+ */
+#define SIMWAVE_HINT_WAVEFIELD_IN_ZERO 1
+#define SIMWAVE_HINT_WAVEFIELD_OUT 2
+#define SIMWAVE_HINT_MODEL_RESIDENT 3
+int simwave_cuda_set_hint(int hint, long long value);
+
+/*
  * Plan API: a problem kept resident on one device.
  *
  * The descriptor carries the same information as the `forward` argument list

@@ -9,6 +9,7 @@
 namespace sw {
 static thread_local std::string g_lastError;
 static thread_local int g_deviceOverride = -1;
+static thread_local long long g_hint[4] = {0, 0, 0, 0};   // indexed by SIMWAVE_HINT_*
 void set_last_error(const std::string &m) { g_lastError = m; }
 
 static double wall()
@@ -22,6 +23,9 @@ static Options current_options()
     Options o = Options::from_env();
     if (g_deviceOverride >= 0)
         o.device = g_deviceOverride;
+    o.zeroIn = g_hint[SIMWAVE_HINT_WAVEFIELD_IN_ZERO] != 0;
+    o.outMode = (int)g_hint[SIMWAVE_HINT_WAVEFIELD_OUT];
+    o.modelToken = g_hint[SIMWAVE_HINT_MODEL_RESIDENT];
     return o;
 }
 
@@ -105,7 +109,24 @@ int simwave_cuda_last_timing_ex(double *out, int n)
     return 6;
 }
 
-void simwave_cuda_release_cache(void) { sw::release_caches(); }
+void simwave_cuda_release_cache(void)
+{
+    sw::drop_resident_models();
+    sw::release_caches();
+}
+
+int simwave_cuda_set_hint(int hint, long long value)
+{
+    if (hint < 1 || hint > 3 ||
+        (hint == SIMWAVE_HINT_WAVEFIELD_OUT && (value < 0 || value > 2))) {
+        sw::set_last_error("simwave_cuda_set_hint: unknown hint or value out of range");
+        return -1;
+    }
+    sw::g_hint[hint] = value;
+    if (hint == SIMWAVE_HINT_MODEL_RESIDENT && value == 0)
+        sw::drop_resident_models();
+    return 0;
+}
 
 unsigned long long simwave_cuda_last_launch_count(void) { return sw::last_timing().launches; }
 

@@ -507,6 +507,46 @@ static void ipc_export(const void *ptr, cudaIpcMemHandle_t *handle, unsigned lon
 }
 
 // ---------------------------------------------------------------------------
+// Model fields of a problem on the device: everything that depends only on
+// velocity / damping / density, the grid and dt.  A plan normally owns its
+// own; under SIMWAVE_HINT_MODEL_RESIDENT (the caller vouches that the model
+// arrays behind a token do not change) the set of the last forward() on a
+// device is kept and handed to the next plan with the same key, so a survey
+// uploads and preprocesses the model once instead of once per shot.
+// ---------------------------------------------------------------------------
+struct ModelKey {
+    long long token = 0;
+    int device = -1, ndim = 0, dtypeBytes = 0, order = 0, math = 0, varden = 0;
+    size_t n[3] = {0, 0, 0};
+    double h[3] = {0, 0, 0}, dt = 0;
+    bool operator==(const ModelKey &o) const
+    {
+        return token == o.token && device == o.device && ndim == o.ndim &&
+               dtypeBytes == o.dtypeBytes && order == o.order && math == o.math &&
+               varden == o.varden && n[0] == o.n[0] && n[1] == o.n[1] && n[2] == o.n[2] &&
+               h[0] == o.h[0] && h[1] == o.h[1] && h[2] == o.h[2] && dt == o.dt;
+    }
+};
+struct ModelFields {
+    ModelKey key;
+    DeviceBuffer c0, q, rho;
+    bool built = false;
+    // tiled 3D kernel extras
+    DeviceBuffer qflags;            // [nS][tilesM][tilesF]: damping profile non-zero in the tile?
+    DeviceBuffer frF, frM, frS;     // first derivatives of the density
+    int tileM = 0, tileF = 0;       // tile the flags were built for (0: not built)
+};
+namespace {
+std::mutex g_residentMu;
+std::map<int, std::shared_ptr<ModelFields>> g_resident;   // per device ordinal
+}
+void drop_resident_models()
+{
+    std::lock_guard<std::mutex> lk(g_residentMu);
+    g_resident.clear();
+}
+
+// ---------------------------------------------------------------------------
 // Plan
 // ---------------------------------------------------------------------------
 template <typename T>
@@ -553,7 +593,8 @@ private:
     size_t numSlots_, stride_, waveletSize_, waveletCount_, nsrc_, nrec_;
     std::vector<char> slotZero_;
 
-    DeviceBuffer c0_, q_, rho_, stage_;
+    std::shared_ptr<ModelFields> model_;
+    DeviceBuffer stage_;
     DeviceBuffer wavelet_, srcIv_, srcVal_, srcOff_, recIv_, recVal_, recOff_, recOut_;
     StepArgs<T> args_;
     PointTables<T> srcTab_, recTab_;
@@ -565,6 +606,8 @@ private:
 
     // tiled 3D kernel (float32, constant density)
     bool useTiled_ = false;
+    bool srcFusedTiled_ = false;   // sources added inside the tiled step kernel
+    size_t stepNow_ = 0;           // time step being launched
     int tiledCfg_ = 0;
     int zChunk_ = 0;
     TiledInfo tiledInfo_{};
@@ -572,11 +615,12 @@ private:
     const CUtensorMap &field_map(const T *base, bool halo);
     void choose_tiling();
     DeviceBuffer loopBarrier_;   // grid barrier word of the persistent 2D loop
-    DeviceBuffer qflags_;   // [nS][tilesM][tilesF]: damping profile non-zero in the tile?
-    DeviceBuffer frF_, frM_, frS_;   // first derivatives of the density (tiled variable density)
 
     cudaStream_t stream_ = nullptr;
     cudaEvent_t evBegin_ = nullptr, evEnd_ = nullptr;
+    cudaStream_t recStream_ = nullptr;     // receiver kernels (nullptr: on stream_)
+    cudaEvent_t recReady_ = nullptr, recDone_ = nullptr;
+    bool recPending_ = false;
 
     // slots
     std::map<size_t, T *> live_;
@@ -672,9 +716,9 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     // scanned on helper threads while the model goes up.  A page-locked `u`
     // with only the three rotating slots is cheaper to upload outright (one
     // DMA at link speed) than to read once with the CPU.
-    slotZero_.assign(numSlots_, 0);
+    slotZero_.assign(numSlots_, opt_.zeroIn ? 1 : 0);
     std::future<void> zeroScan;
-    if (!(numSlots_ == 3 && is_pinned_host(hostU_)))
+    if (!opt_.zeroIn && !(numSlots_ == 3 && is_pinned_host(hostU_)))
         zeroScan = std::async(std::launch::async, [this] {
             if (all_zero(hostU_, numSlots_ * denseCells_ * sizeof(T))) {
                 std::fill(slotZero_.begin(), slotZero_.end(), 1);
@@ -693,6 +737,11 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     SW_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     SW_CUDA(cudaEventCreate(&evBegin_));
     SW_CUDA(cudaEventCreate(&evEnd_));
+    if (pb.num_receivers && !opt_.debug && !env_is("SIMWAVE_CUDA_RECEIVERS", "inline")) {
+        SW_CUDA(cudaStreamCreateWithFlags(&recStream_, cudaStreamNonBlocking));
+        SW_CUDA(cudaEventCreateWithFlags(&recReady_, cudaEventDisableTiming));
+        SW_CUDA(cudaEventCreateWithFlags(&recDone_, cudaEventDisableTiming));
+    }
     phases.mark("context+stream");
 
     // ---- static part of the step arguments ------------------------------
@@ -753,22 +802,50 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     volatile T dtsqv = dt * dt;   // rounded in T, like `f_type dtSquared = dt * dt`
     const T dtsq = dtsqv;
 
-    new_field(c0_);
-    new_field(q_);
-    stage_.alloc(2 * denseCells_ * sizeof(T));
-    T *stageA = stage_.as<T>(), *stageB = stage_.as<T>() + denseCells_;
-    h2d(stageA, pb.velocity, denseCells_ * sizeof(T));
-    h2d(stageB, pb.damp, denseCells_ * sizeof(T));
-    model_kernel<T><<<row_grid(g), 256, 0, stream_>>>(g, stageA, stageB, dt, dtsq,
-                                                      field_base(c0_), field_base(q_));
-    check_launch("model_kernel");
-    if (varden_) {
-        new_field(rho_);
-        upload_dense((const T *)pb.density, field_base(rho_));
+    // resident model of an earlier forward() with the same key, or a fresh one
+    {
+        ModelKey key;
+        key.token = opt_.modelToken;
+        key.device = device_; key.ndim = ndim_; key.dtypeBytes = (int)sizeof(T);
+        key.order = (int)pb.space_order; key.math = opt_.math; key.varden = varden_ ? 1 : 0;
+        key.n[0] = pb.nz; key.n[1] = pb.nx; key.n[2] = ndim_ == 3 ? pb.ny : 1;
+        key.h[0] = pb.dz; key.h[1] = pb.dx; key.h[2] = ndim_ == 3 ? pb.dy : 0;
+        key.dt = pb.dt;
+        if (opt_.modelToken != 0) {
+            std::lock_guard<std::mutex> lk(g_residentMu);
+            auto it = g_resident.find(device_);
+            if (it != g_resident.end() && it->second->key == key && it->second.use_count() == 1)
+                model_ = it->second;
+            else {
+                model_ = std::make_shared<ModelFields>();
+                model_->key = key;
+                g_resident[device_] = model_;   // replaces (and frees) any other model
+            }
+        } else {
+            model_ = std::make_shared<ModelFields>();
+            model_->key = key;
+        }
     }
-    a.c0 = field_base(c0_);
-    a.q = field_base(q_);
-    a.rho = varden_ ? field_base(rho_) : nullptr;
+    if (!model_->built) {
+        new_field(model_->c0);
+        new_field(model_->q);
+        stage_.alloc(2 * denseCells_ * sizeof(T));
+        T *stageA = stage_.as<T>(), *stageB = stage_.as<T>() + denseCells_;
+        h2d(stageA, pb.velocity, denseCells_ * sizeof(T));
+        h2d(stageB, pb.damp, denseCells_ * sizeof(T));
+        model_kernel<T><<<row_grid(g), 256, 0, stream_>>>(g, stageA, stageB, dt, dtsq,
+                                                          field_base(model_->c0),
+                                                          field_base(model_->q));
+        check_launch("model_kernel");
+        if (varden_) {
+            new_field(model_->rho);
+            upload_dense((const T *)pb.density, field_base(model_->rho));
+        }
+        model_->built = true;
+    }
+    a.c0 = field_base(model_->c0);
+    a.q = field_base(model_->q);
+    a.rho = varden_ ? field_base(model_->rho) : nullptr;
     phases.mark("model alloc+enqueue");
 
     // ---- wavelet and tables -------------------------------------------------
@@ -875,6 +952,12 @@ template <typename T>
 Plan<T>::~Plan()
 {
     drain_.reset();   // joins the worker before buffers go away
+    if (recStream_) {
+        cudaStreamSynchronize(recStream_);
+        cudaStreamDestroy(recStream_);
+        cudaEventDestroy(recReady_);
+        cudaEventDestroy(recDone_);
+    }
     if (stream_) {
         cudaStreamSynchronize(stream_);
         cudaStreamDestroy(stream_);
@@ -1084,27 +1167,37 @@ void Plan<T>::choose_tiling()
         }
         zChunk_ = std::max(1, std::min(zchunk, interior));
         useTiled_ = true;
+        // few sources whose windows lie among the interior points: the step
+        // kernel adds them itself (SIMWAVE_CUDA_SOURCES=kernel keeps the launch)
+        srcFusedTiled_ = srcInterior_ && nsrc_ <= 8 && srcMode_ != SRC_ATOMIC &&
+                         !env_is("SIMWAVE_CUDA_SOURCES", "kernel");
 
         // per (plane, tile) flag: does the damping profile act inside the tile?
-        qflags_.alloc((size_t)g_.nS * tilesM * tilesF);
-        SW_CUDA(cudaMemsetAsync(qflags_.get(), 0, qflags_.bytes(), stream_));
-        dim3 grid((unsigned)tilesF, (unsigned)tilesM, (unsigned)interior);
-        qflag_kernel<<<grid, 128, 0, stream_>>>(g_, field_base(q_), tiledInfo_.tileM(),
-                                                tiledInfo_.tileF(),
-                                                qflags_.as<unsigned char>());
-        check_launch("qflag_kernel");
-        if (varden_) {
-            new_field(frF_);
-            new_field(frM_);
-            new_field(frS_);
-            dim3 gg((g_.nF - 2 * r + 127) / 128, g_.nM - 2 * r, interior);
-            if (opt_.math == MATH_STRICT)
-                rho_gradient_kernel<float, MATH_STRICT><<<gg, 128, 0, stream_>>>(
-                    args_, field_base(frF_), field_base(frM_), field_base(frS_));
-            else
-                rho_gradient_kernel<float, MATH_FAST><<<gg, 128, 0, stream_>>>(
-                    args_, field_base(frF_), field_base(frM_), field_base(frS_));
-            check_launch("rho_gradient_kernel");
+        if (model_->tileM != tiledInfo_.tileM() || model_->tileF != tiledInfo_.tileF()) {
+            model_->qflags.alloc((size_t)g_.nS * tilesM * tilesF);
+            SW_CUDA(cudaMemsetAsync(model_->qflags.get(), 0, model_->qflags.bytes(), stream_));
+            dim3 grid((unsigned)tilesF, (unsigned)tilesM, (unsigned)interior);
+            qflag_kernel<<<grid, 128, 0, stream_>>>(g_, field_base(model_->q), tiledInfo_.tileM(),
+                                                    tiledInfo_.tileF(),
+                                                    model_->qflags.as<unsigned char>());
+            check_launch("qflag_kernel");
+            if (varden_ && !model_->frF.get()) {
+                new_field(model_->frF);
+                new_field(model_->frM);
+                new_field(model_->frS);
+                dim3 gg((g_.nF - 2 * r + 127) / 128, g_.nM - 2 * r, interior);
+                if (opt_.math == MATH_STRICT)
+                    rho_gradient_kernel<float, MATH_STRICT><<<gg, 128, 0, stream_>>>(
+                        args_, field_base(model_->frF), field_base(model_->frM),
+                        field_base(model_->frS));
+                else
+                    rho_gradient_kernel<float, MATH_FAST><<<gg, 128, 0, stream_>>>(
+                        args_, field_base(model_->frF), field_base(model_->frM),
+                        field_base(model_->frS));
+                check_launch("rho_gradient_kernel");
+            }
+            model_->tileM = tiledInfo_.tileM();
+            model_->tileF = tiledInfo_.tileF();
         }
         if (std::getenv("SIMWAVE_CUDA_VERBOSE"))
             std::fprintf(stderr,
@@ -1159,13 +1252,22 @@ void Plan<T>::launch_step(const StepArgs<T> &a)
             maps.q = field_map(a.q, false);
             if (varden_) {
                 maps.rho = field_map(a.rho, false);
-                maps.frF = field_map(field_base(frF_), false);
-                maps.frM = field_map(field_base(frM_), false);
-                maps.frS = field_map(field_base(frS_), false);
+                maps.frF = field_map(field_base(model_->frF), false);
+                maps.frM = field_map(field_base(model_->frM), false);
+                maps.frS = field_map(field_base(model_->frS), false);
+            }
+            maps.srcFused = srcFusedTiled_ ? 1 : 0;
+            maps.src = srcTab_;
+            maps.wavelet = wavelet_.as<float>();
+            maps.waveletCount = (int)waveletCount_;
+            maps.step = (long long)stepNow_;
+            for (int ax = 0; ax < 3; ax++) {
+                maps.srcLo[ax] = srcBox_[ax][0];
+                maps.srcHi[ax] = srcBox_[ax][1];
             }
             auto launch = [&](const StepArgs<T> &args) {
                 if (!kTiledLaunch[g_.r](tiledCfg_, varden_, opt_.math, args, maps,
-                                        qflags_.as<unsigned char>(), zChunk_, stream_))
+                                        model_->qflags.as<unsigned char>(), zChunk_, stream_))
                     throw Error("tiled kernel configuration vanished");
                 check_launch("tiled step kernel");
             };
@@ -1180,7 +1282,7 @@ void Plan<T>::launch_step(const StepArgs<T> &a)
 template <typename T>
 void Plan<T>::launch_sources(const StepArgs<T> &a, size_t n)
 {
-    if (!nsrc_)
+    if (!nsrc_ || srcFusedTiled_)
         return;
     dim3 grid((srcMaxPoints_ + 127) / 128, (unsigned)std::min<size_t>(nsrc_, 65535), 1);
     if (ndim_ == 3)
@@ -1192,6 +1294,11 @@ void Plan<T>::launch_sources(const StepArgs<T> &a, size_t n)
     check_launch("source_kernel");
 }
 
+// Receivers of step n sample U^n (= `cur`), which step n only reads: the
+// kernel runs on a side stream beside the step kernel.  It starts once step
+// n-1 has been stored (event on the compute stream); the compute stream in
+// turn makes step n+1 wait for it (event on the side stream), long before
+// any kernel overwrites the slot.
 template <typename T>
 void Plan<T>::launch_receivers(const T *cur, size_t n)
 {
@@ -1199,11 +1306,33 @@ void Plan<T>::launch_receivers(const T *cur, size_t n)
         return;
     T *row = recOut_.as<T>() + (n - 1) * nrec_;
     const unsigned blocks = (unsigned)((nrec_ * 32 + 127) / 128);
-    if (ndim_ == 3)
-        receiver_kernel<T, 3><<<blocks, 128, 0, stream_>>>(g_, cur, recTab_, row);
-    else
-        receiver_kernel<T, 2><<<blocks, 128, 0, stream_>>>(g_, cur, recTab_, row);
+    cudaStream_t st = stream_;
+    if (recStream_) {
+        // step n's kernels (queued after this call) wait for every earlier
+        // receiver launch: whatever slot they overwrite has been sampled
+        if (recPending_)
+            SW_CUDA(cudaStreamWaitEvent(stream_, recDone_, 0));
+        SW_CUDA(cudaEventRecord(recReady_, stream_));
+        SW_CUDA(cudaStreamWaitEvent(recStream_, recReady_, 0));
+        st = recStream_;
+    }
+    const bool strict = opt_.math == MATH_STRICT;
+    if (ndim_ == 3) {
+        if (strict)
+            receiver_kernel<T, 3, MATH_STRICT><<<blocks, 128, 0, st>>>(g_, cur, recTab_, row);
+        else
+            receiver_kernel<T, 3, MATH_FAST><<<blocks, 128, 0, st>>>(g_, cur, recTab_, row);
+    } else {
+        if (strict)
+            receiver_kernel<T, 2, MATH_STRICT><<<blocks, 128, 0, st>>>(g_, cur, recTab_, row);
+        else
+            receiver_kernel<T, 2, MATH_FAST><<<blocks, 128, 0, st>>>(g_, cur, recTab_, row);
+    }
     check_launch("receiver_kernel");
+    if (recStream_) {
+        SW_CUDA(cudaEventRecord(recDone_, recStream_));
+        recPending_ = true;
+    }
 }
 
 template <typename T>
@@ -1267,6 +1396,7 @@ void Plan<T>::run(size_t begin, size_t end)
 
         if (slabUp_ || slabDown_)
             slab_wait(n);
+        stepNow_ = n;
         launch_receivers(a.cur, n);
         launch_step(a);
         launch_sources(a, n);
@@ -1299,6 +1429,10 @@ void Plan<T>::run(size_t begin, size_t end)
         }
     }
     recEnd_ = std::max(recEnd_, end);
+    if (recPending_) {
+        SW_CUDA(cudaStreamWaitEvent(stream_, recDone_, 0));   // the loop ends with its receivers
+        recPending_ = false;
+    }
     SW_CUDA(cudaEventRecord(evEnd_, stream_));
     SW_CUDA(cudaEventSynchronize(evEnd_));
     if (slabUp_ || slabDown_) {
@@ -1379,9 +1513,14 @@ void Plan<T>::download(void *u, void *receivers)
     T *saveU = hostU_;
     if (u)
         hostU_ = (T *)u;
+    // which slots the caller wants back: all of them (the ABI's contract),
+    // or -- SIMWAVE_HINT_WAVEFIELD_OUT, three rotating slots only -- just slot
+    // end_timestep % 3 (the one simwave's Solver returns, model.py:639-641),
+    // or none
     std::vector<size_t> slots;
     for (auto &kv : live_)
-        slots.push_back(kv.first);
+        if (stride_ != 0 || opt_.outMode == 0 || (opt_.outMode == 1 && kv.first == curT_))
+            slots.push_back(kv.first);
     for (size_t s : slots)
         retire(s, true);
     drain_->wait_idle();

@@ -23,6 +23,10 @@ struct Options {
     int prefetch;      // planes of L2 prefetch ahead of the tiled kernel's ring loads (-1: default)
     bool perStep;      // 2D: per-step launches instead of the persistent loop kernel
     int device;        // -1: current
+    // promises of the caller (simwave_cuda_set_hint), all off by default
+    bool zeroIn = false;        // every slot of u is zero on entry
+    int outMode = 0;            // slots copied back: 0 all, 1 slot end_timestep % 3 only, 2 none
+    long long modelToken = 0;   // != 0: model arrays unchanged while the token is
     static Options from_env();
 };
 
@@ -126,6 +130,8 @@ public:
     virtual void slab_connect(const void *up, const void *down) = 0;
     Timing timing;
 };
+
+void drop_resident_models();
 
 std::unique_ptr<PlanBase> make_plan(const simwave_problem &pb, const Options &opt);
 

@@ -51,6 +51,17 @@ struct StepMaps {
     // planes by which the producer warp runs ahead with L2 prefetches of every
     // input tile (cp.async.bulk.prefetch.tensor; 0 = none, at most 32)
     int prefetch;
+    // Sources added by the thread that owns the cell, right after its stencil
+    // value and before the boundary-aware store (the reference's own order:
+    // section 1, section 2, section 3 of the loop): used when every window lies
+    // among the interior points and the sources are few.  srcLo / srcHi: the
+    // bounding box of all windows, (S,M,F).
+    int srcFused;
+    PointTables<float> src;
+    const float *wavelet;
+    int waveletCount;
+    long long step;
+    int srcLo[3], srcHi[3];
 };
 #define SW_DECL_TILED(R)                                                              \
     bool tiled3d_query_r##R(int cfg, bool varden, int math, TiledInfo *info);                   \

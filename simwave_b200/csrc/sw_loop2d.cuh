@@ -229,7 +229,20 @@ loop2d_persistent_kernel(const __grid_constant__ LoopArgs<T> L)
         // loop): per step only the wavefield samples are loaded
         if (L.rec.count) {
             T *row = L.recOut + (n - 1) * L.rec.count;
-            if (recCached) {
+            if (recCached && MATH != MATH_STRICT) {
+                // receiver_sample_fast with the weights already in registers
+                T acc = T(0);
+                for (int im = 0; im < recNM; im++) {
+                    const T wm = __shfl_sync(0xffffffffu, recWM, im & 31);
+                    if (lane < recNF)
+                        acc = Ops<T>::fma(cur[g.at(0, recLoM + im, recLoF + lane)], wm, acc);
+                }
+                acc = (lane < recNF) ? Ops<T>::mul(Ops<T>::fma(acc, T(1), T(0)), recWF) : T(0);
+                for (int d = 16; d > 0; d >>= 1)
+                    acc = Ops<T>::add(acc, __shfl_xor_sync(0xffffffffu, acc, d));
+                if (lane == 0)
+                    row[gwarp] = acc;
+            } else if (recCached) {
                 T sum = T(0);
                 constexpr int BATCH = 4;
                 for (int r0 = 0; r0 < recNM; r0 += BATCH) {
@@ -254,7 +267,9 @@ loop2d_persistent_kernel(const __grid_constant__ LoopArgs<T> L)
             }
             for (long long rec = recCached ? gwarp + nwarps : gwarp; rec < L.rec.count;
                  rec += nwarps) {
-                const T sum = receiver_sample<T, 2>(g, cur, L.rec, (int)rec, lane);
+                const T sum = (MATH == MATH_STRICT)
+                                  ? receiver_sample<T, 2>(g, cur, L.rec, (int)rec, lane)
+                                  : receiver_sample_fast<T, 2>(g, cur, L.rec, (int)rec, lane);
                 if (lane == 0)
                     row[rec] = sum;
             }

@@ -328,7 +328,35 @@ __device__ __forceinline__ T receiver_sample(const Grid &g, const T *cur,
     return sum;
 }
 
+// FAST mode: every lane sums its own column of the window (F offset = lane)
+// over the rows with FMAs, then the lanes are added pairwise.  The serial
+// chain above costs one shuffle and one dependent add per window point (729
+// for a half-width of 4: ~35 us per launch); this one 81 FMAs and 5 shuffles.
+// The sum is the same up to the rounding of a different association.
 template <typename T, int NDIM>
+__device__ __forceinline__ T receiver_sample_fast(const Grid &g, const T *cur,
+                                                  const PointTables<T> &tab, int rec, int lane)
+{
+    const Window<T, NDIM> win(tab, rec);
+    T acc = T(0);
+    if (lane < win.n[2]) {
+        const T wf = win.w[2][lane];
+        for (int is = 0; is < win.n[0]; is++) {
+            const T ws = (NDIM == 3) ? win.w[0][is] : T(1);
+            T part = T(0);
+            for (int im = 0; im < win.n[1]; im++)
+                part = Ops<T>::fma(cur[g.at(win.lo[0] + is, win.lo[1] + im, win.lo[2] + lane)],
+                                   win.w[1][im], part);
+            acc = Ops<T>::fma(part, ws, acc);
+        }
+        acc = Ops<T>::mul(acc, wf);
+    }
+    for (int d = 16; d > 0; d >>= 1)
+        acc = Ops<T>::add(acc, __shfl_xor_sync(0xffffffffu, acc, d));
+    return acc;
+}
+
+template <typename T, int NDIM, int MATH>
 __global__ void receiver_kernel(Grid g, const T *__restrict__ cur, PointTables<T> tab,
                                 T *__restrict__ row)
 {
@@ -336,7 +364,8 @@ __global__ void receiver_kernel(Grid g, const T *__restrict__ cur, PointTables<T
     const int rec = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (rec >= tab.count)
         return;
-    const T sum = receiver_sample<T, NDIM>(g, cur, tab, rec, lane);
+    const T sum = (MATH == MATH_STRICT) ? receiver_sample<T, NDIM>(g, cur, tab, rec, lane)
+                                        : receiver_sample_fast<T, NDIM>(g, cur, tab, rec, lane);
     if (lane == 0)
         row[rec] = sum;
 }

@@ -39,6 +39,7 @@
 
 #include "sw_launch.h"
 #include "sw_math.cuh"
+#include "sw_points.cuh"
 #include "sw_step_simple.cuh"
 
 namespace sw {
@@ -245,6 +246,30 @@ static __device__ __noinline__ void store_row_special(const StepArgs<float> &a, 
             if (alt)
                 alt[p + c] = o4[c];
         }
+    }
+}
+
+// Section 2 of the reference loop for the four cells (s, m, f .. f+3) of one
+// thread: every source whose window covers a cell adds its term, in index
+// order, each add rounded on its own (3d/wave.c:208-295).  Rare path (only
+// tiles and planes inside the bounding box of the windows get here).
+static __device__ __noinline__ void add_sources_row4(const StepMaps &maps, int s, int m, int f,
+                                                     const float c0v[4], const float qv[4],
+                                                     float v[4])
+{
+    for (int src = 0; src < maps.src.count; src++) {
+        long long wo = maps.step - 1;
+        if (maps.waveletCount > 1)
+            wo = (maps.step - 1) * maps.src.count + src;
+        const float w = maps.wavelet[wo];
+        if (w == 0.0f)
+            continue;
+        const Window<float, 3> win(maps.src, src);
+        for (int c = 0; c < 4; c++)
+            if (win.contains(s, m, f + c)) {
+                const float kws = win.weight(s - win.lo[0], m - win.lo[1], f + c - win.lo[2]);
+                v[c] = Ops<float>::add(v[c], source_term<float>(c0v[c], qv[c], kws, w));
+            }
     }
 }
 
@@ -480,6 +505,11 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
         keep[i] = k;
     }
     float *outRow = a.next + g.at(z0, m0 + ty * PM, fMine);
+    // does a source window reach into this tile? (CTA-uniform)
+    const bool srcTile = maps.srcFused && m0 <= maps.srcHi[AX_M] &&
+                         m0 + TL::BX - 1 >= maps.srcLo[AX_M] && f0 <= maps.srcHi[AX_F] &&
+                         f0 + TL::BY - 1 >= maps.srcLo[AX_F] && z0 <= maps.srcHi[AX_S] &&
+                         z1 - 1 >= maps.srcLo[AX_S];
 
     // the plane loop is unrolled UNR times so that the queue shift turns into
     // register renaming inside the unrolled body
@@ -651,6 +681,22 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 for (int h = 0; h < 2; h++)
                     out[i][h] = update_pair<MATH, false>(lap[h], qv[i][h][R], pvv[h], c0a[h],
                                                          make_float2(0.0f, 0.0f));
+            }
+            if (srcTile && s >= maps.srcLo[AX_S] && s <= maps.srcHi[AX_S]) {
+                const int m = m0 + ty * PM + i;
+                if (m >= maps.srcLo[AX_M] && m <= maps.srcHi[AX_M] &&
+                    fMine <= maps.srcHi[AX_F] && fMine + 3 >= maps.srcLo[AX_F]) {
+                    float qs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    if (hasQ) {
+                        const float4 qd = *reinterpret_cast<const float4 *>(sQ + off);
+                        qs[0] = qd.x; qs[1] = qd.y; qs[2] = qd.z; qs[3] = qd.w;
+                    }
+                    const float cs[4] = {cv.x, cv.y, cv.z, cv.w};
+                    float v[4] = {out[i][0].x, out[i][0].y, out[i][1].x, out[i][1].y};
+                    add_sources_row4(maps, s, m, fMine, cs, qs, v);
+                    out[i][0] = make_float2(v[0], v[1]);
+                    out[i][1] = make_float2(v[2], v[3]);
+                }
             }
         }
 

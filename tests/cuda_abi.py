@@ -11,12 +11,12 @@ import sys
 import numpy as np
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for _p in (REPO, os.path.join(REPO, "oracle")):
+for _p in (REPO, os.path.dirname(os.path.abspath(__file__))):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
 from simwave_b200.kernel.backend.compiler import prebuilt_library  # noqa: E402
-import oracle  # noqa: E402  (only for abi_args/_argtypes: the ABI is shared)
+from abi import forward_args, forward_argtypes  # noqa: E402
 
 _libs = {}
 
@@ -29,7 +29,7 @@ def shim(ndim, density, dtype):
             "-DFLOAT" if np.dtype(dtype) == np.float32 else "-DDOUBLE")
         lib = ctypes.CDLL(path)
         lib.forward.restype = ctypes.c_double
-        lib.forward.argtypes = oracle._argtypes(ndim, density, dtype)
+        lib.forward.argtypes = forward_argtypes(ndim, density, dtype)
         _libs[key] = lib
     return _libs[key]
 
@@ -56,7 +56,7 @@ def cuda_forward(p):
     """Run problem dict ``p`` in place through the shim's `forward`."""
     lib = shim(p["velocity"].ndim, p.get("density") is not None,
                p["velocity"].dtype)
-    seconds = lib.forward(*oracle.abi_args(p))
+    seconds = lib.forward(*forward_args(p))
     if seconds < 0:
         raise RuntimeError(core().simwave_cuda_last_error().decode())
     return seconds

@@ -14,6 +14,7 @@ the sharpest check of the loop structure, boundary logic, source ordering and
 snapshot plumbing; the *_default_math tests repeat the sweep in the default
 mode against the tolerance.
 """
+import ctypes
 import os
 import sys
 
@@ -495,3 +496,137 @@ def test_persistent_2d_loop_every_radius(order, density, dtype, monkeypatch):
     assert np.abs(per_step["u"]).max() > 0
     assert np.array_equal(per_step["u"], persistent["u"])
     assert np.array_equal(per_step["receivers"], persistent["receivers"])
+
+
+# ---------------------------------------------------------------------------
+# data-path hints (include/simwave_cuda.h, simwave_cuda_set_hint) and the fused
+# small kernels: exact, so everything is compared bit for bit
+# ---------------------------------------------------------------------------
+HINT_ZERO_IN, HINT_OUT, HINT_MODEL = 1, 2, 3
+
+
+@pytest.fixture
+def hints():
+    lib = core()
+    lib.simwave_cuda_set_hint.argtypes = [ctypes.c_int, ctypes.c_longlong]
+
+    def set_hint(key, value):
+        assert lib.simwave_cuda_set_hint(key, value) == 0
+    yield set_hint
+    for key in (HINT_ZERO_IN, HINT_OUT, HINT_MODEL):
+        lib.simwave_cuda_set_hint(key, 0)
+
+
+@pytest.mark.parametrize("shape,order", [((44, 40, 48), 8), ((60, 72), 4)])
+def test_hints_change_the_data_path_not_the_results(shape, order, hints, monkeypatch):
+    monkeypatch.setenv("SIMWAVE_CUDA_MATH", "fast")
+    T = 25
+    p = problems.make_problem(shape=shape, space_order=order, timesteps=T, seed=21,
+                              nbl=((0, 3),) * len(shape))
+    base = problems.clone(p)
+    cuda_forward(base)
+    # zero wavefield on entry + only the slot the Solver returns
+    hints(HINT_ZERO_IN, 1)
+    hints(HINT_OUT, 1)
+    q = problems.clone(p)
+    q["u"][...] = np.nan          # never read
+    cuda_forward(q)
+    keep = T % 3
+    assert np.array_equal(q["u"][keep], base["u"][keep])
+    assert all(np.isnan(q["u"][s]).all() for s in range(3) if s != keep)
+    assert np.array_equal(q["receivers"], base["receivers"])
+    # receivers only
+    hints(HINT_OUT, 2)
+    q = problems.clone(p)
+    q["u"][...] = np.nan
+    cuda_forward(q)
+    assert np.isnan(q["u"]).all()
+    assert np.array_equal(q["receivers"], base["receivers"])
+    # unknown hints are refused
+    assert core().simwave_cuda_set_hint(9, 1) == -1
+    assert core().simwave_cuda_set_hint(HINT_OUT, 5) == -1
+
+
+def test_resident_model_serves_the_next_shots(hints, monkeypatch):
+    """A survey under one model token: the second shot (other source and
+    receiver tables) reuses the device model; results equal fresh runs.  A
+    changed model under a NEW token is picked up."""
+    monkeypatch.setenv("SIMWAVE_CUDA_MATH", "fast")
+    shape = (40, 44, 48)
+    shots = []
+    for k, seed in enumerate((3, 4)):
+        p = problems.make_problem(shape=shape, space_order=8, timesteps=20, seed=31,
+                                  density=True, nbl=((0, 4), (3, 3), (4, 2)))
+        q = problems.make_problem(shape=shape, space_order=8, timesteps=20, seed=seed,
+                                  density=True, nbl=((0, 4), (3, 3), (4, 2)))
+        for key in ("src_intervals", "src_values", "src_offsets", "rec_intervals",
+                    "rec_values", "rec_offsets", "wavelet"):
+            p[key] = q[key]
+        shots.append(p)
+    assert np.array_equal(shots[0]["velocity"], shots[1]["velocity"])
+    fresh = [problems.clone(s) for s in shots]
+    for f in fresh:
+        cuda_forward(f)
+    hints(HINT_MODEL, 77)
+    for s, f in zip(shots, fresh):
+        got = problems.clone(s)
+        cuda_forward(got)
+        assert np.array_equal(got["u"], f["u"])
+        assert np.array_equal(got["receivers"], f["receivers"])
+    # a stale model would be wrong here: other velocity under the same token is
+    # the caller's broken promise, under a new token it must be re-read
+    other = problems.clone(shots[0])
+    other["velocity"] *= np.float32(1.02)
+    want = problems.clone(other)
+    hints(HINT_MODEL, 0)
+    cuda_forward(want)
+    hints(HINT_MODEL, 78)
+    got = problems.clone(other)
+    cuda_forward(got)
+    assert np.array_equal(got["u"], want["u"])
+    assert not np.array_equal(got["u"], fresh[0]["u"])
+
+
+@pytest.mark.parametrize("math", ["strict", "fast"])
+def test_sources_fused_into_the_step_kernel_match_the_source_kernel(math, monkeypatch):
+    """Tiled 3D kernel: interior source windows are added by the thread that
+    owns the cell; same bits as the stand-alone source kernel, next to a
+    Neumann face, with overlapping windows and per-source wavelets."""
+    monkeypatch.setenv("SIMWAVE_CUDA_MATH", math)
+    r = 4
+    shape = (40, 48, 80)
+    src = [(r + 3.3, 20.2, 30.7), (r + 4.1, 21.0, 31.4), (30.5, 40.2, 70.9)]
+    p = problems.make_problem(shape=shape, space_order=2 * r, timesteps=14, seed=5,
+                              bc=(2, 1, 2, 1, 1, 2), nbl=((0, 3), (3, 3), (3, 3)),
+                              num_sources=3, src_positions=src, multi_wavelet=True,
+                              src_radius=3)
+    fused = problems.clone(p)
+    cuda_forward(fused)
+    launches_fused = core().simwave_cuda_last_launch_count()
+    monkeypatch.setenv("SIMWAVE_CUDA_SOURCES", "kernel")
+    separate = problems.clone(p)
+    cuda_forward(separate)
+    assert core().simwave_cuda_last_launch_count() == launches_fused + 14
+    assert np.abs(fused["u"]).max() > 0
+    assert np.array_equal(fused["u"], separate["u"])
+    assert np.array_equal(fused["receivers"], separate["receivers"])
+    if math == "strict":
+        ref = problems.clone(p)
+        oracle.forward(ref)
+        assert_identical(ref, fused)
+
+
+@pytest.mark.parametrize("shape", [(36, 40, 44), (50, 64)])
+def test_receivers_on_the_side_stream_match_inline_launches(shape, monkeypatch):
+    monkeypatch.setenv("SIMWAVE_CUDA_MATH", "fast")
+    monkeypatch.setenv("SIMWAVE_CUDA_LOOP", "launch")
+    p = problems.make_problem(shape=shape, space_order=4, timesteps=30, seed=12,
+                              num_receivers=40)
+    side = problems.clone(p)
+    cuda_forward(side)
+    monkeypatch.setenv("SIMWAVE_CUDA_RECEIVERS", "inline")
+    inline = problems.clone(p)
+    cuda_forward(inline)
+    assert np.abs(side["receivers"]).max() > 0
+    assert np.array_equal(side["receivers"], inline["receivers"])
+    assert np.array_equal(side["u"], inline["u"])

@@ -14,13 +14,21 @@ model, space order 8, constant density, float32, 207x801x801 grid
 Printed JSON line (rank 0):
   value     Gpts/s with the problem resident in HBM, timed with CUDA events on
             the stream the kernels are launched on (max over ranks)
-  e2e       the same metric through the drop-in `forward` C-ABI with host
-            buffers: H2D of the model, time loop, D2H of the wavefield slots
-            and receiver traces, wall clock around the call
+  e2e       the same metric through the drop-in `forward` C-ABI with pinned
+            host buffers: H2D of the model, time loop, D2H of the wavefield
+            slots and receiver traces, wall clock around the call
+  e2e_pageable / e2e_api  (N = 1) the same call with pageable NumPy arrays,
+            and simwave_b200.Solver.forward() of the public API, front end
+            included
   roofline  algorithmic bytes (20 B per grid-point update)
             / device time against the measured HBM peak
   cpu_baseline  the reference's cpu_openmp kernel (oracle/_ref) on a bounded
             number of time steps of the same arrays, on this host's cores
+  slab / slab_strong  C4-shaped variable-density so-16 model split into z-slabs
+            over the ranks: 1024 owned planes per GPU (weak), and the 1040^3
+            grid itself split N ways (strong, N > 1)
+  survey    C5: 64 shots x 512^3 through forward(), shot s on rank s mod N
+  configs_2d  (N = 1) C1 and C2: device loop, forward() and the CPU kernel
 
 `--impl reference` times the reference's own CPU implementation alone.
 Under torchrun every rank simulates its own shot of the workload (shot
@@ -36,7 +44,9 @@ import threading
 import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
-for _p in (REPO, os.path.join(REPO, "tests"), os.path.join(REPO, "oracle")):
+# tests/ holds the ctypes callers of the C-ABI (cuda_abi.py, abi.py); oracle/
+# is put on the path only by the CPU legs (cpu_reference_run)
+for _p in (REPO, os.path.join(REPO, "tests")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
@@ -65,14 +75,24 @@ def parse():
                     help="skip the slab-decomposition leg")
     ap.add_argument("--slab-only", action="store_true",
                     help="run only the slab-decomposition leg and print it")
-    ap.add_argument("--slab-planes", type=int, default=512,
-                    help="owned z-planes per GPU in the slab leg")
+    ap.add_argument("--slab-planes", type=int, default=1024,
+                    help="owned z-planes per GPU in the weak-scaling slab leg "
+                         "(1024 = the 1024^3-per-GPU configuration of BASELINE.md)")
+    ap.add_argument("--no-slab-strong", action="store_true",
+                    help="skip the strong-scaling leg (C4 proper: 1040^3 split "
+                         "over the ranks), which runs when N > 1")
     ap.add_argument("--slab-n", type=int, default=1040)
     ap.add_argument("--slab-timesteps", type=int, default=60)
-    ap.add_argument("--shots", type=int, default=0,
-                    help="C5 survey leg (with --workload shot_3d): this many "
-                         "shots over one shared model, dealt round-robin to the "
-                         "ranks, each through the drop-in forward()")
+    ap.add_argument("--shots", type=int, default=64,
+                    help="C5 survey leg: this many shots over one shared 512^3 "
+                         "model, dealt round-robin to the ranks, each through "
+                         "the drop-in forward()")
+    ap.add_argument("--shot-timesteps", type=int, default=300)
+    ap.add_argument("--no-survey", action="store_true")
+    ap.add_argument("--no-2d", action="store_true",
+                    help="skip the two 2D configurations (C1, C2; N = 1 only)")
+    ap.add_argument("--no-api", action="store_true",
+                    help="skip the e2e_api leg (Solver.forward, N = 1 only)")
     return ap.parse_args()
 
 
@@ -162,10 +182,25 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
+def set_cpu_threads():
+    """All host cores for the CPU arm.  torchrun exports OMP_NUM_THREADS=1 and
+    libgomp may already be initialised by the time the CPU leg runs, so the
+    count is set in the environment AND through the OpenMP runtime."""
+    n = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except (OSError, AttributeError):
+        pass
+    return n
+
+
 def cpu_reference_run(p, timesteps, variant="ompfast"):
     """Reference CPU kernel on the first `timesteps` steps of problem p."""
+    oracle_dir = os.path.join(REPO, "oracle")
+    if oracle_dir not in sys.path:
+        sys.path.insert(0, oracle_dir)
     import oracle
-    import problems
     kind = oracle.best_kind()
     if kind == "ref" and not oracle.available("ref", p["velocity"].ndim,
                                               p.get("density") is not None,
@@ -178,7 +213,6 @@ def cpu_reference_run(p, timesteps, variant="ompfast"):
     q["receivers"] = np.zeros_like(p["receivers"])
     q["end_timestep"] = timesteps
     seconds = oracle.forward(q, kind=kind, variant=variant)
-    del problems
     return seconds, kind, variant
 
 
@@ -204,7 +238,7 @@ def run_reference(args, p, rank, world):
         return
     pts = workloads.interior_points(p)
     sample = args.cpu_timesteps or max(1, int(3e9 // pts))
-    os.environ.setdefault("OMP_NUM_THREADS", str(host_threads()))
+    set_cpu_threads()
     times = []
     for i in range(args.warmup + args.steps):
         s, kind, variant = cpu_reference_run(p, sample)
@@ -231,6 +265,19 @@ def run_reference(args, p, rank, world):
     print(json.dumps(line))
 
 
+def l2_policy(p):
+    """How the timing rules' L2 clause is met by this workload: a time step
+    streams five fields (u_prev, u_cur, u_next, c0, q [+ density terms])."""
+    field = p["velocity"].nbytes
+    if 5 * field > 2 * 126e6:
+        return ("inputs larger than L2 (each field %.0f MiB, a time step streams "
+                ">= 5 of them; no flush needed)" % (field / 2 ** 20))
+    return ("working set %.1f MiB fits the 126 MB L2 by the nature of the "
+            "configuration: consecutive time steps of one loop reuse it, "
+            "nothing is flushed, and the roofline fraction says nothing about "
+            "DRAM" % (5 * field / 2 ** 20))
+
+
 def workload_config(args, p, timesteps):
     return {
         "workload": "%s: grid %s (extended, halo %d), space_order %d, %s "
@@ -240,8 +287,7 @@ def workload_config(args, p, timesteps):
                         p["space_order"] // 2, p["space_order"],
                         "variable" if p.get("density") is not None else "constant",
                         timesteps, len(p["rec_offsets"]) - 1),
-        "l2_policy": "inputs larger than L2 (each field %.0f MiB)"
-                     % (p["velocity"].nbytes / 2 ** 20),
+        "l2_policy": l2_policy(p),
         "parallelism": "shot-parallel, one shot per GPU" if args.gpus > 1
                        else "single GPU",
     }
@@ -262,15 +308,18 @@ def pinned_like(a):
 out_keepalive = []
 
 
-def run_slab_leg(args, rank, world, dist, barrier, max_over_ranks):
+def run_slab_leg(args, rank, world, dist, barrier, max_over_ranks, planes=None,
+                 scaling="weak"):
     """One large 3D model split into z-slabs, one per GPU, ghost planes kept
     current on the device over NVLink (simwave_b200/slab.py).  Weak scaling:
-    --slab-planes owned planes per GPU.  Returns the "slab" object of the
-    bench line (None on ranks other than 0)."""
+    --slab-planes owned planes per GPU; strong scaling: `planes` = 1024 / N (C4
+    proper, the 1040^3 grid).  Returns the "slab" object of the bench line
+    (None on ranks other than 0)."""
     import workloads
     from simwave_b200 import slab
+    planes = planes or args.slab_planes
     q = workloads.slab_3d(rank=rank, world=world,
-                          planes_per_gpu=args.slab_planes, n=args.slab_n,
+                          planes_per_gpu=planes, n=args.slab_n,
                           timesteps=args.slab_timesteps)
     r = q["space_order"] // 2
     T = q["end_timestep"]
@@ -299,7 +348,7 @@ def run_slab_leg(args, rank, world, dist, barrier, max_over_ranks):
     peak, _ = measured_peak()
     value = world * pts * T * len(times) / total / 1e9
     return {
-        "value": value, "unit": "Gpts/s", "scaling": "weak",
+        "value": value, "unit": "Gpts/s", "scaling": scaling,
         "ms_per_timestep": 1e3 * total / len(times) / T,
         "roofline_frac_per_gpu": value / world * bpp / peak,
         "config": {
@@ -315,13 +364,27 @@ def run_slab_leg(args, rank, world, dist, barrier, max_over_ranks):
     }
 
 
-def run_survey_leg(args, p, rank, world, barrier, max_over_ranks):
-    """C5: a multi-shot survey.  The model stays on the host once per rank
-    (page-locked); every shot is one drop-in forward() call with its own
-    tables, wavefield and traces; shot s runs on rank s mod world.  No
-    data-path collective.  Returns the "survey" object of the bench line."""
+def set_hints(lib, **hints):
+    """simwave_cuda_set_hint by name (include/simwave_cuda.h)."""
+    codes = {"wavefield_in_zero": 1, "wavefield_out": 2, "model_resident": 3}
+    lib.simwave_cuda_set_hint.argtypes = [ctypes.c_int, ctypes.c_longlong]
+    for name, value in hints.items():
+        if lib.simwave_cuda_set_hint(codes[name], int(value)) != 0:
+            raise RuntimeError("hint %s refused" % name)
+
+
+def run_survey_leg(args, rank, world, barrier, max_over_ranks):
+    """C5: a multi-shot survey (64 shots x 512^3, so 8, a 512-receiver line per
+    shot, 300 steps).  The model stays on the host once per rank (page-locked);
+    every shot is one drop-in forward() call with its own tables, wavefield and
+    traces; shot s runs on rank s mod world.  No data-path collective.  The
+    survey driver tells the library what it knows about its own arrays
+    (simwave_cuda_set_hint): `u` is zero on entry, only the traces are wanted
+    back, and the model is the same for every shot.  Returns the "survey"
+    object of the bench line."""
     import workloads
-    from cuda_abi import cuda_forward
+    from cuda_abi import core, cuda_forward, last_timing
+    p = workloads.shot_3d(shot=0, timesteps=args.shot_timesteps)
     T = p["end_timestep"]
     pts = workloads.interior_points(p)
     host = dict(p)
@@ -331,36 +394,115 @@ def run_survey_leg(args, p, rank, world, barrier, max_over_ranks):
     host["receivers"] = pinned_like(p["receivers"])
     mine = list(range(rank, args.shots, world))
     traces = {}
+    device_seconds = []
+    lib = core()
 
     def shoot(shot):
         q = workloads.reshoot(p, shot)
         for key in ("src_intervals", "src_values", "src_offsets",
                     "rec_intervals", "rec_values", "rec_offsets"):
             host[key] = q[key]
-        host["u"][...] = 0
         host["receivers"][...] = 0
         cuda_forward(host)
+        device_seconds.append(last_timing()["loop"])
         traces[shot] = float(np.abs(host["receivers"]).max())
 
-    if mine:
-        shoot(mine[0])                      # warm-up: allocation caches, clocks
-    barrier()
-    t0 = time.perf_counter()
-    for shot in mine:
-        shoot(shot)
-    seconds = time.perf_counter() - t0
-    barrier()
+    set_hints(lib, wavefield_in_zero=1, wavefield_out=2, model_resident=1000 + rank)
+    try:
+        if mine:
+            shoot(mine[0])                  # warm-up: model upload, caches, clocks
+        barrier()
+        device_seconds.clear()
+        t0 = time.perf_counter()
+        for shot in mine:
+            shoot(shot)
+        seconds = time.perf_counter() - t0
+        barrier()
+    finally:
+        set_hints(lib, wavefield_in_zero=0, wavefield_out=0, model_resident=0)
+        lib.simwave_cuda_release_cache()
     total = max_over_ranks(seconds)
+    device_total = max_over_ranks(sum(device_seconds))
     if rank != 0:
         return None
-    return {"value": args.shots * pts * T / total / 1e9, "unit": "Gpts/s",
+    work = args.shots * pts * T / 1e9
+    return {"value": work / total, "unit": "Gpts/s",
+            "device_value": work / device_total,
+            "e2e_over_device": device_total / total,
             "shots": args.shots, "shots_per_second": args.shots / total,
             "seconds": total, "scaling": "strong",
             "config": {"workload": "survey of %d shots over %s" % (
                 args.shots, workload_config(args, p, T)["workload"]),
                 "parallelism": "shot s on rank s mod %d, one forward() per "
-                               "shot, model arrays shared on the host" % world},
+                               "shot, model arrays shared on the host" % world,
+                "hints": "wavefield_in_zero, wavefield_out=none (traces only), "
+                         "model_resident (one model upload per rank)",
+                "note": "value = through forward() with host buffers, wall "
+                        "clock (max over ranks); device_value = the same shots' "
+                        "CUDA-event loop time"},
             "max_abs_trace_of_first_shot": traces.get(0)}
+
+
+def run_2d_config(name, args, barrier):
+    """C1 / C2 on one GPU: device-resident loop (plan API, CUDA events), the
+    drop-in forward() with pageable host arrays, and the reference's
+    cpu_openmp kernel on the whole run, for the "configs_2d" object."""
+    import workloads
+    from cuda_abi import cuda_forward
+    from simwave_b200 import slab
+    p = workloads.WORKLOADS[name]()
+    T = p["end_timestep"]
+    pts = workloads.interior_points(p)
+    plan = slab.Plan(p)
+    times = []
+    for i in range(3 + max(2, args.steps)):
+        plan.reset()
+        t = plan.run(1, T)
+        if i >= 3:
+            times.append(t)
+    launches = plan.launches()
+    plan.destroy()
+    dev = sum(times) / len(times)
+    e2e = []
+    for i in range(3):
+        q = dict(p)
+        q["u"] = np.zeros_like(p["u"])
+        q["receivers"] = np.zeros_like(p["receivers"])
+        barrier()
+        t0 = time.perf_counter()
+        cuda_forward(q)
+        e2e.append(time.perf_counter() - t0)
+    out = {
+        "value": pts * T / dev / 1e9, "unit": "Gpts/s",
+        "us_per_timestep": 1e6 * dev / T, "timesteps": T,
+        "e2e": {"value": pts * T / min(e2e[1:]) / 1e9, "unit": "Gpts/s",
+                "host_memory": "pageable (NumPy)",
+                "h2d_bytes_per_step": int(sum(
+                    p[k].nbytes for k in ("velocity", "damp", "wavelet", "src_values",
+                                          "rec_values", "src_intervals",
+                                          "rec_intervals"))),
+                "d2h_bytes_per_step": int(p["u"].nbytes + p["receivers"].nbytes)},
+        "gpu_launches_per_step": int(launches),
+        "config": workload_config(args, p, T),
+        "roofline_note": "frac vs HBM would be %.2f of the measured peak, but "
+                         "the fields live in L2 (see l2_policy): the loop is "
+                         "bound by per-step latency (one cooperative launch, a "
+                         "grid barrier per step), not DRAM" % (
+                             pts * T / dev * workloads.bytes_per_point(p) / 1e9
+                             / measured_peak()[0]),
+    }
+    if not args.no_cpu:
+        try:
+            set_cpu_threads()
+            cpu_reference_run(p, min(T, 20))
+            sec, kind, variant = cpu_reference_run(p, T)
+            out["cpu_baseline"] = {
+                "value": pts * T / sec / 1e9, "unit": "Gpts/s", "cores": host_threads(),
+                "kind": "reference" if kind == "ref" else "port",
+                "sample": "all %d time steps, %s build, OMP_PROC_BIND=true" % (T, variant)}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "sample": "failed: %s" % e}
+    return out
 
 
 def run_ours(args, p, rank, world, local_rank):
@@ -431,27 +573,9 @@ def run_ours(args, p, rank, world, local_rank):
     peak, peak_kind = measured_peak()
 
     # ---- end to end through the drop-in forward() ---------------------------
-    e2e = None
-    if not args.no_e2e:
-        host = dict(p)
-        for key in ("velocity", "damp", "density", "wavelet"):
-            if host.get(key) is not None:
-                host[key] = pinned_like(host[key])
-        host["u"] = pinned_like(p["u"])
-        host["receivers"] = pinned_like(p["receivers"])
-        h2d = sum(host[k].nbytes for k in
-                  ("velocity", "damp", "wavelet", "src_intervals", "src_values",
-                   "src_offsets", "rec_intervals", "rec_values", "rec_offsets"))
-        if host.get("density") is not None:
-            h2d += host["density"].nbytes
-        if host["u"].shape[0] == 3:
-            # a page-locked three-slot wavefield is uploaded outright (cheaper
-            # than scanning it for zeros on the host)
-            h2d += host["u"].nbytes
-        d2h = host["u"].nbytes + host["receivers"].nbytes
-        e2e_warm = max(1, min(args.warmup, 1))
+    def time_forward(host, calls, warm):
         times = []
-        for i in range(e2e_warm + args.steps):
+        for i in range(warm + calls):
             host["u"][...] = 0
             host["receivers"][...] = 0
             barrier()
@@ -459,22 +583,114 @@ def run_ours(args, p, rank, world, local_rank):
             cuda_forward(host)
             torch.cuda.synchronize()
             dt_wall = time.perf_counter() - t0
-            if i >= e2e_warm:
+            if i >= warm:
                 times.append(dt_wall)
+        return times
+
+    def abi_bytes(host, pinned):
+        h2d = sum(host[k].nbytes for k in
+                  ("velocity", "damp", "wavelet", "src_intervals", "src_values",
+                   "src_offsets", "rec_intervals", "rec_values", "rec_offsets"))
+        if host.get("density") is not None:
+            h2d += host["density"].nbytes
+        if pinned and host["u"].shape[0] == 3:
+            # a page-locked three-slot wavefield is uploaded outright (cheaper
+            # than scanning it for zeros on the host);
+            # a pageable one is scanned and, being zero, never uploaded
+            h2d += host["u"].nbytes
+        return int(h2d), int(host["u"].nbytes + host["receivers"].nbytes)
+
+    e2e = e2e_pageable = e2e_api = None
+    if not args.no_e2e:
+        host = dict(p)
+        for key in ("velocity", "damp", "density", "wavelet"):
+            if host.get(key) is not None:
+                host[key] = pinned_like(host[key])
+        host["u"] = pinned_like(p["u"])
+        host["receivers"] = pinned_like(p["receivers"])
+        h2d, d2h = abi_bytes(host, True)
+        times = time_forward(host, args.steps, 1)
         tm = last_timing()
         e2e_total = max_over_ranks(sum(times))
         e2e = {"value": world * pts * T * len(times) / e2e_total / 1e9,
-               "unit": "Gpts/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h),
+               "unit": "Gpts/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h,
                "seconds_per_step": e2e_total / len(times),
                "breakdown_last_call": tm,
-               "host_memory": "pinned (torch pin_memory)"}
+               "host_memory": "pinned (torch pin_memory)",
+               "call": "drop-in forward() C-ABI, every slot of u copied back"}
+        del host
+        out_keepalive.clear()
+
+    if not args.no_e2e and world == 1:
+        # the same call with the pageable NumPy arrays simwave's Solver passes
+        host = dict(p)
+        host["u"] = np.zeros_like(p["u"])
+        host["receivers"] = np.zeros_like(p["receivers"])
+        h2d, d2h = abi_bytes(host, False)
+        times = time_forward(host, max(1, args.steps), 1)
+        e2e_pageable = {"value": pts * T * len(times) / sum(times) / 1e9,
+                        "unit": "Gpts/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h,
+                        "seconds_per_step": sum(times) / len(times),
+                        "breakdown_last_call": last_timing(),
+                        "host_memory": "pageable (NumPy)",
+                        "call": "drop-in forward() C-ABI, every slot of u copied back"}
+        del host
+
+    if not args.no_e2e and not args.no_api and world == 1 and \
+            p["name"] in workloads._API_SPECS:
+        # the call a simwave user makes: Solver.forward() of the public API,
+        # front end included in the timed region (tables, kernel arguments,
+        # halo stripping); the model objects are built once, as a user would
+        import contextlib
+        try:
+            t0 = time.perf_counter()
+            solver = workloads.api_solver(
+                p["name"], timesteps=T if args.timesteps else None)
+            build_s = time.perf_counter() - t0
+            steps_api = solver.time_model.timesteps
+            times = []
+            for i in range(1 + max(1, args.steps)):
+                barrier()
+                t0 = time.perf_counter()
+                with contextlib.redirect_stdout(sys.stderr):
+                    u_api, rec_api = solver.forward()
+                torch.cuda.synchronize()
+                if i >= 1:
+                    times.append(time.perf_counter() - t0)
+            space = solver.space_model
+            e2e_api = {
+                "value": pts * steps_api * len(times) / sum(times) / 1e9,
+                "unit": "Gpts/s", "seconds_per_step": sum(times) / len(times),
+                "timesteps": steps_api,
+                # model resident after the warm-up call: wavelet and tables go up,
+                # one extended wavefield slot and the shot record come back
+                "h2d_bytes_per_step": int(
+                    solver.wavelet.values.nbytes + sum(
+                        a.nbytes for acq in (solver.sources, solver.receivers)
+                        for a in acq.interpolated_points_and_values)),
+                "d2h_bytes_per_step": int(
+                    np.prod(space.extended_shape) * u_api.itemsize + rec_api.nbytes),
+                "breakdown_last_call": last_timing(),
+                "model_build_seconds_not_timed": build_s,
+                "host_memory": "pageable (NumPy)",
+                "call": "simwave_b200.Solver.forward() (SpaceModel, TimeModel, "
+                        "Source, Receiver, RickerWavelet as in the reference's "
+                        "benchmark script); model resident on the device after "
+                        "the warm-up call (SpaceModel.model_token), u known to "
+                        "be zero on entry, only the returned wavefield slot and "
+                        "the shot record copied back",
+                "max_abs_wavefield": float(np.abs(u_api).max())}
+            del solver, u_api, rec_api
+        except Exception as e:       # an extra leg must not sink the bench line
+            e2e_api = {"error": "%s: %s" % (type(e).__name__, e)}
 
     # ---- CPU baseline beside it (rank 0, N == 1 only) ------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sample = args.cpu_timesteps or max(1, int(3e9 // pts))
-        os.environ.setdefault("OMP_NUM_THREADS", str(host_threads()))
+        set_cpu_threads()
         try:
             cpu_reference_run(p, 1)      # warm the pages / threads
             s, kind, variant = cpu_reference_run(p, sample)
@@ -488,20 +704,40 @@ def run_ours(args, p, rank, world, local_rank):
             cpu = {"value": None, "unit": "Gpts/s", "cores": host_threads(),
                    "kind": "port", "sample": "failed: %s" % e}
 
-    # ---- slab decomposition leg (C4-shaped, weak scaling) --------------------
-    slab_result = None
+    # ---- slab decomposition legs (C4-shaped) ---------------------------------
+    slab_result = slab_strong = None
     if not args.no_slab:
         try:
             slab_result = run_slab_leg(args, rank, world, dist, barrier,
                                        max_over_ranks)
+            if world > 1 and not args.no_slab_strong and 1024 % world == 0:
+                slab_strong = run_slab_leg(args, rank, world, dist, barrier,
+                                           max_over_ranks, planes=1024 // world,
+                                           scaling="strong")
         except Exception as e:      # the extra leg must not sink the bench line
             if world > 1:
                 raise               # ranks wait on each other: fail together
             slab_result = {"error": "%s: %s" % (type(e).__name__, e)}
 
+    # ---- C5: multi-shot survey through forward() ------------------------------
     survey = None
-    if args.shots > 0 and p["name"] == "shot_3d":
-        survey = run_survey_leg(args, p, rank, world, barrier, max_over_ranks)
+    if args.shots > 0 and not args.no_survey:
+        try:
+            survey = run_survey_leg(args, rank, world, barrier, max_over_ranks)
+        except Exception as e:
+            if world > 1:
+                raise
+            survey = {"error": "%s: %s" % (type(e).__name__, e)}
+
+    # ---- C1 / C2: the 2D configurations (N == 1) -------------------------------
+    configs_2d = None
+    if world == 1 and not args.no_2d:
+        configs_2d = {}
+        for name in ("readme_2d", "marmousi_2d"):
+            try:
+                configs_2d[name] = run_2d_config(name, args, barrier)
+            except Exception as e:
+                configs_2d[name] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank == 0:
         line = {
@@ -524,8 +760,12 @@ def run_ours(args, p, rank, world, local_rank):
                         "the loop (source and receiver kernels included)" % bpp},
             "cpu_baseline": cpu,
             "e2e": e2e,
+            "e2e_pageable": e2e_pageable,
+            "e2e_api": e2e_api,
             "slab": slab_result,
+            "slab_strong": slab_strong,
             "survey": survey,
+            "configs_2d": configs_2d,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "wall_ms_per_step": 1e3 * wall / args.steps,

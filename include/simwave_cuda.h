@@ -246,7 +246,9 @@ void simwave_cuda_release_cache(void);
  *      caller: velocity / damp / density, the grid, dt and space_order are the
  *      same for every call made under this token, so the device keeps the
  *      preprocessed model of the last call (per device) and the next one skips
- *      its upload.  A new token, 0, or simwave_cuda_release_cache() drops it.
+ *      its upload.  0 switches the lookup off for the following calls; the
+ *      device copy goes when a call under another token replaces it or with
+ *      simwave_cuda_release_cache().
  *
  * Returns 0, or -1 for an unknown hint / value (see simwave_cuda_last_error).
  */

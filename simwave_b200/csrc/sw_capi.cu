@@ -123,8 +123,6 @@ int simwave_cuda_set_hint(int hint, long long value)
         return -1;
     }
     sw::g_hint[hint] = value;
-    if (hint == SIMWAVE_HINT_MODEL_RESIDENT && value == 0)
-        sw::drop_resident_models();
     return 0;
 }
 

@@ -7,13 +7,16 @@ pinned by the reference's tests/test_compiler.py.  The difference is what
 ``compile()`` does for ``language='cuda'``: the reference shells out to nvcc
 on its cuda/wave.cu (compiler.py:150-152, 209-227); here it returns the path
 of a *prebuilt* sm_100a library from simwave_b200/lib/ and never runs a
-compiler.  This package ships no CPU kernels: the other languages are only
-honoured for a user-supplied ``cfile`` (the reference's custom-kernel hook,
-compiler.py:157-159), which is compiled and cached the same way the reference
-does it.
+compiler.  This package ships no CPU kernels: with a user-supplied ``cfile``
+(the reference's custom-kernel hook, compiler.py:157-159) the other languages
+compile and cache that file the way the reference does; without one they run
+on the prebuilt CUDA backend too, with a warning (so that the reference's
+examples and its default ``Compiler()`` work unmodified), or are refused with
+SIMWAVE_B200_STRICT_LANGUAGE=1.  Nothing ever runs the time loop on the CPU.
 """
 import os
 import subprocess
+import warnings
 from hashlib import sha1
 
 LANGUAGES = ('c', 'cpu_openmp', 'gpu_openmp', 'gpu_openacc', 'cuda')
@@ -24,6 +27,8 @@ _OPENMP_FLAG = {'gcc': '-fopenmp', 'icc': '-openmp',
 _LANGUAGE_MACRO = {'cpu_openmp': '-DCPU_OPENMP', 'gpu_openmp': '-DGPU_OPENMP',
                    'gpu_openacc': '-DGPU_OPENACC'}
 _PRECISION_TAG = {'-DFLOAT': 'f32', '-DDOUBLE': 'f64'}
+
+_WARNED_LANGUAGES = set()
 
 LIB_DIR = os.path.join(
     os.path.dirname(os.path.dirname(os.path.dirname(
@@ -149,11 +154,25 @@ class Compiler:
                                         operator)
 
         if self.language != 'cuda':
-            raise NotImplementedError(
-                "simwave_b200 ships only the prebuilt CUDA (sm_100a) backend: "
-                "use Compiler(language='cuda'), or pass cfile= to build a "
-                "custom kernel with language={!r}.".format(self.language)
-            )
+            # The reference's examples, benchmarks and its default
+            # Compiler() ask for 'c' / 'cpu_openmp' / 'gpu_*' kernels, which
+            # this package does not ship.  They still run: on the prebuilt
+            # CUDA backend, never on the CPU, and say so once per language.
+            if os.environ.get('SIMWAVE_B200_STRICT_LANGUAGE') == '1':
+                raise NotImplementedError(
+                    "simwave_b200 ships only the prebuilt CUDA (sm_100a) "
+                    "backend: use Compiler(language='cuda'), or pass cfile= to "
+                    "build a custom kernel with language={!r}."
+                    .format(self.language)
+                )
+            if self.language not in _WARNED_LANGUAGES:
+                _WARNED_LANGUAGES.add(self.language)
+                warnings.warn(
+                    "simwave_b200 has no {!r} kernels: running on the prebuilt "
+                    "CUDA (sm_100a) backend instead; cc and cflags are "
+                    "ignored.".format(self.language), RuntimeWarning,
+                    stacklevel=2
+                )
 
         path = prebuilt_library(dimension, density, float_precision)
         if not os.path.exists(path):

@@ -50,6 +50,9 @@ _CTYPE = {
 
 _PRECISION_MACRO = {'float32': '-DFLOAT', 'float64': '-DDOUBLE'}
 
+# include/simwave_cuda.h: SIMWAVE_HINT_*
+_HINT_CODE = {'wavefield_in_zero': 1, 'wavefield_out': 2, 'model_resident': 3}
+
 
 class Middleware:
     """
@@ -64,6 +67,9 @@ class Middleware:
     def __init__(self, compiler):
         self._compiler = Compiler(language='cuda') if compiler is None \
             else compiler
+        # promises of the caller about the arrays of the next exec(), by name
+        # (see _HINT_CODE); applied around the call and withdrawn after it
+        self.hints = {}
 
     @property
     def compiler(self):
@@ -135,7 +141,12 @@ class Middleware:
         forward.restype = ctypes.c_double
         forward.argtypes = [types[k] for k in keys]
 
-        exec_time = forward(*[kwargs[k] for k in keys])
+        hinted = self._apply_hints(lib, self.hints)
+        try:
+            exec_time = forward(*[kwargs[k] for k in keys])
+        finally:
+            self._apply_hints(lib, dict.fromkeys(hinted, 0))
+            self.hints = {}
 
         if exec_time < 0:
             raise RuntimeError(
@@ -145,6 +156,26 @@ class Middleware:
         print('Run forward in %f seconds.' % exec_time)
 
         return kwargs.get('u_full'), kwargs.get('shot_record')
+
+    @staticmethod
+    def _apply_hints(lib, hints):
+        """Hand data-path hints to a library that takes them (the prebuilt
+        CUDA backend); a custom kernel built from ``cfile`` has no such entry
+        point and is simply called as the reference would.  Returns the names
+        that were set."""
+        if not hints:
+            return []
+        try:
+            setter = lib.simwave_cuda_set_hint
+        except AttributeError:
+            return []
+        setter.restype = ctypes.c_int
+        setter.argtypes = [ctypes.c_int, ctypes.c_longlong]
+        done = []
+        for name, value in hints.items():
+            if setter(_HINT_CODE[name], int(value)) == 0:
+                done.append(name)
+        return done
 
     @staticmethod
     def _last_error(lib):

@@ -8,12 +8,18 @@ density, damping mask, FD weights, dt, number of timesteps), so each value is
 produced with the same NumPy operations on the same dtypes as the reference.
 The code is written once for any dimension instead of per-2D/3D branches.
 """
+import itertools
+
 import numpy as np
 from scipy.interpolate import RegularGridInterpolator
 
 from simwave_b200.kernel.frontend import fd
 
 _BC_NAMES = ('none', 'null_dirichlet', 'null_neumann')
+
+# tokens of the extended-model arrays handed to the kernel (see
+# SpaceModel.model_token); unique per process, never 0
+_MODEL_TOKENS = itertools.count(1)
 
 
 class SpaceModel:
@@ -57,6 +63,13 @@ class SpaceModel:
         self._velocity_model = self.interpolate(velocity_model)
         self._density_model = None if density_model is None \
             else self.interpolate(density_model)
+        # The resampled models belong to this object and never change after
+        # construction (the reference has no setter either): read-only, so
+        # that the extended arrays derived from them can be kept (below).
+        self._velocity_model.flags.writeable = False
+        if self._density_model is not None:
+            self._density_model.flags.writeable = False
+        self._extended = {}
 
     # ---- plain attributes -------------------------------------------------
     @property
@@ -271,36 +284,69 @@ class SpaceModel:
         )
         return np.pad(array=array, pad_width=widths, mode=mode)
 
+    def _kept(self, name, build):
+        """The extended array ``name``, built once per boundary configuration.
+
+        The reference rebuilds these arrays on every access (twice per
+        ``Solver.forward`` for the velocity of a 10^8-point model: seconds of
+        ``numpy.pad``).  They only depend on the (read-only) models and on
+        what ``config_boundary`` set, so they are kept, read-only, until that
+        changes; ``model_token`` changes with them."""
+        signature = (self.nbl, self.halo_size, self.damping_polynomial_degree,
+                     self.damping_alpha)
+        entry = self._extended.get(name)
+        if entry is None or entry[0] != signature:
+            array = build()
+            if array is not None:
+                array.flags.writeable = False
+            self._extended[name] = entry = (signature, array)
+            self._model_token = next(_MODEL_TOKENS)
+        return entry[1]
+
+    @property
+    def model_token(self):
+        """Identifies the current set of extended arrays (velocity, density,
+        damping mask): a new value whenever one of them is rebuilt.  The CUDA
+        backend keeps the preprocessed model of the last ``forward`` on the
+        device under this token (SIMWAVE_HINT_MODEL_RESIDENT), so a survey of
+        many shots over one SpaceModel uploads the model once."""
+        self.extended_velocity_model, self.extended_density_model, self.damping_mask
+        return self._model_token
+
     @property
     def damping_mask(self):
         """
         Damping coefficient per extended grid point: zero in the physical
         domain and in the halo, ``alpha * d**degree`` in the layers, d being
         the distance in grid points from the physical domain
-        (reference model.py:378-406).
+        (reference model.py:378-406).  Read-only; kept between accesses.
         """
-        mask = np.pad(
-            array=np.zeros(self.shape, dtype=self.dtype),
-            pad_width=self.nbl_pad_width,
-            mode="linear_ramp",
-            end_values=self.nbl_pad_width
-        )
-        mask = (mask ** self.damping_polynomial_degree) * self.damping_alpha
-        return np.pad(array=mask, pad_width=self.halo_pad_width)
+        def build():
+            mask = np.pad(
+                array=np.zeros(self.shape, dtype=self.dtype),
+                pad_width=self.nbl_pad_width,
+                mode="linear_ramp",
+                end_values=self.nbl_pad_width
+            )
+            mask = (mask ** self.damping_polynomial_degree) * self.damping_alpha
+            return np.pad(array=mask, pad_width=self.halo_pad_width)
+        return self._kept('damping_mask', build)
 
     @property
     def extended_velocity_model(self):
         """Velocity edge-padded over layers and halo
-        (reference model.py:421-441)."""
-        return self._pad(self.velocity_model, mode="edge")
+        (reference model.py:421-441).  Read-only; kept between accesses."""
+        return self._kept('velocity',
+                          lambda: self._pad(self.velocity_model, mode="edge"))
 
     @property
     def extended_density_model(self):
         """Density edge-padded over layers and halo, or None
-        (reference model.py:444-466)."""
+        (reference model.py:444-466).  Read-only; kept between accesses."""
         if self.density_model is None:
             return None
-        return self._pad(self.density_model, mode="edge")
+        return self._kept('density',
+                          lambda: self._pad(self.density_model, mode="edge"))
 
     # ---- output trimming --------------------------------------------------
     def _trim(self, u, widths):

@@ -128,6 +128,17 @@ class Solver:
         arguments.update(self._table_arguments('src', self.sources))
         arguments.update(self._table_arguments('rec', self.receivers))
 
+        # What this call knows about its own arrays, for the CUDA backend's
+        # data path (include/simwave_cuda.h, simwave_cuda_set_hint): u_full is
+        # freshly allocated zeros; with saving_stride == 0 only slot
+        # timesteps % 3 is handed back below; the extended model arrays are
+        # the SpaceModel's read-only ones, unchanged while its token is.
+        self._middleware.hints = {
+            'wavefield_in_zero': 1,
+            'wavefield_out': 1 if time.saving_stride == 0 else 0,
+            'model_resident': space.model_token,
+        }
+
         u_full, recv = self._middleware.exec(operator='forward', **arguments)
 
         u_full = time.remove_time_halo_region(u_full)

@@ -60,12 +60,19 @@ def test_compiler_returns_prebuilt_library_for_cuda():
     assert os.path.exists(path)
 
 
-def test_no_cpu_fallback():
-    """Languages other than cuda are refused unless a custom kernel file is
-    supplied; nothing silently runs on the CPU."""
-    with pytest.raises(NotImplementedError):
-        api.Compiler(language="c").compile(2, "constant_density", "-DFLOAT",
-                                           "forward")
+def test_no_cpu_fallback(monkeypatch):
+    """No language ever selects a CPU kernel: without a custom kernel file the
+    reference's other languages are served by the prebuilt CUDA library (with
+    a warning, so the reference's examples run unmodified), or refused under
+    SIMWAVE_B200_STRICT_LANGUAGE=1."""
+    with pytest.warns(RuntimeWarning, match="CUDA"):
+        path = api.Compiler(language="c").compile(2, "constant_density", "-DFLOAT",
+                                                  "forward")
+    assert path.endswith("libsimwave_cuda_2d_constant_f32.so")
+    path = api.Compiler(cc="gcc", language="cpu_openmp", cflags="-O3 -fPIC").compile(
+        3, "variable_density", "-DDOUBLE", "forward")
+    assert path.endswith("libsimwave_cuda_3d_variable_f64.so")
+    monkeypatch.setenv("SIMWAVE_B200_STRICT_LANGUAGE", "1")
     with pytest.raises(NotImplementedError):
         api.Compiler(language="cpu_openmp").compile(3, "variable_density",
                                                     "-DDOUBLE", "forward")

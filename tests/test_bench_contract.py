@@ -80,3 +80,27 @@ def test_product_never_touches_the_oracle():
     lib = os.path.join(REPO, "simwave_b200", "lib", "libsimwave_b200.so")
     needed = subprocess.run(["readelf", "-d", lib], capture_output=True, text=True).stdout
     assert "oracle" not in needed and "ref_" not in needed
+
+
+def test_cpu_arm_uses_every_host_core_even_under_torchrun(monkeypatch):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must not inherit it
+    (round-1 SCALE records at N >= 2 ran the reference single-threaded)."""
+    import ctypes
+    sys.path.insert(0, REPO)
+    import bench
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    gomp = ctypes.CDLL("libgomp.so.1")
+    gomp.omp_set_num_threads(1)
+    n = bench.set_cpu_threads()
+    assert n == bench.host_threads() >= 1
+    assert os.environ["OMP_NUM_THREADS"] == str(n)
+    assert gomp.omp_get_max_threads() == n
+
+
+def test_cuda_arm_imports_nothing_from_the_oracle():
+    """tests/cuda_abi.py and tests/abi.py (the ctypes callers bench.py's GPU arm
+    and smoke() use) are independent of oracle/."""
+    for name in ("cuda_abi.py", "abi.py"):
+        with open(os.path.join(REPO, "tests", name)) as f:
+            text = f.read()
+        assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), name

@@ -127,3 +127,73 @@ def test_batched_tables_equal_one_by_one(half_width, dtype):
         assert np.array_equal(np.diff(offsets.astype(np.int64)),
                               [b.size for _, b in one])
         assert iv.dtype == np.uint and weights.dtype == np.float32
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_batched_tables_equal_one_by_one_tables(dtype):
+    """The batched table builder promotes `index - position` like the
+    one-by-one path for either model precision (NumPy >= 2 scalar rules, the
+    floor this package states in README.md)."""
+    from simwave_b200.kernel.frontend import kws
+    assert int(np.__version__.split(".")[0]) >= 2
+    rng = np.random.default_rng(7)
+    shape = (60, 75, 90)
+    locations = (rng.random((40, 3)) * (np.array(shape) - 1)).astype(dtype)
+    iv, values, offsets = kws.get_source_points_batch(shape, locations, 4)
+    for i, location in enumerate(locations):
+        p, v = kws.get_source_points(shape, [dtype(x) for x in location], 4)
+        assert np.array_equal(iv[6 * i:6 * i + 6], p)
+        assert np.array_equal(values[int(offsets[i]):int(offsets[i + 1])], v)
+
+
+def test_extended_arrays_are_kept_until_the_boundary_configuration_changes():
+    vel = np.linspace(1500, 3000, 30 * 40, dtype=np.float32).reshape(30, 40)
+    sm = api.SpaceModel((0, 290, 0, 390), (10, 10), vel, density_model=vel / 2,
+                        space_order=4)
+    sm.config_boundary(damping_length=(0, 30, 20, 20),
+                       boundary_condition="null_dirichlet")
+    v1, d1, m1, t1 = (sm.extended_velocity_model, sm.extended_density_model,
+                      sm.damping_mask, sm.model_token)
+    assert sm.extended_velocity_model is v1 and sm.damping_mask is m1
+    assert sm.extended_density_model is d1 and sm.model_token == t1 != 0
+    for a in (v1, d1, m1, sm.velocity_model, sm.density_model):
+        assert not a.flags.writeable
+        with pytest.raises(ValueError):
+            a[0, 0] = 1
+    # same values as a fresh build
+    fresh = api.SpaceModel((0, 290, 0, 390), (10, 10), vel, density_model=vel / 2,
+                           space_order=4)
+    fresh.config_boundary(damping_length=(0, 30, 20, 20),
+                          boundary_condition="null_dirichlet")
+    assert np.array_equal(fresh.extended_velocity_model, v1)
+    assert np.array_equal(fresh.damping_mask, m1)
+    assert fresh.model_token != t1
+    # a new configuration rebuilds them under a new token
+    sm.config_boundary(damping_length=40, boundary_condition="none")
+    assert sm.extended_velocity_model is not v1
+    assert sm.extended_velocity_model.shape == sm.extended_shape
+    assert sm.model_token != t1
+
+
+def test_middleware_withdraws_its_hints_after_the_call():
+    """Solver.forward's data-path hints travel through
+    simwave_cuda_set_hint around the call only."""
+    from simwave_b200.kernel.backend.middleware import Middleware
+
+    class Setter:            # stands in for the ctypes function object
+        def __init__(self):
+            self.calls = []
+
+        def __call__(self, key, value):
+            self.calls.append((key, value))
+            return 0
+
+    class FakeLib:
+        simwave_cuda_set_hint = Setter()
+
+    lib = FakeLib()
+    done = Middleware._apply_hints(lib, {'wavefield_in_zero': 1, 'model_resident': 42})
+    assert done == ['wavefield_in_zero', 'model_resident']
+    Middleware._apply_hints(lib, dict.fromkeys(done, 0))
+    assert lib.simwave_cuda_set_hint.calls == [(1, 1), (3, 42), (1, 0), (3, 0)]
+    assert Middleware._apply_hints(object(), {'wavefield_out': 1}) == []

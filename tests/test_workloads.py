@@ -67,3 +67,35 @@ def test_survey_shots_share_the_model_and_move_the_acquisition():
         assert again["shot"] == shot
     assert not np.array_equal(workloads.reshoot(base, 1)["src_intervals"],
                               base["src_intervals"])
+
+
+def test_api_solvers_hand_the_kernel_the_arrays_of_the_abi_builders(monkeypatch):
+    """bench.py's e2e_api leg (workloads.api_solver: the reference's benchmark
+    scripts through simwave_b200's public API) runs the same problem as the
+    ABI-level builders: every kernel argument agrees bit for bit."""
+    from simwave_b200.kernel.backend import middleware
+    seen = {}
+
+    def capture(self, **kwargs):
+        seen.update(kwargs)
+        return kwargs['u_full'], kwargs['shot_record']
+    monkeypatch.setattr(middleware.Middleware, "_exec_forward", capture)
+    for name in ("readme_2d", "marmousi_2d"):
+        p = workloads.WORKLOADS[name]()
+        solver = workloads.api_solver(name)
+        u, rec = solver.forward()
+        assert rec.shape == p["receivers"].shape
+        assert np.array_equal(seen["velocity_model"], p["velocity"])
+        assert np.array_equal(seen["damping_mask"], p["damp"])
+        assert np.array_equal(seen["wavelet"], p["wavelet"])
+        assert seen["dt"] == p["dt"] and seen["end_timestep"] == p["end_timestep"]
+        assert np.array_equal(seen["second_order_fd_coefficients"], p["coeff2"])
+        for a, b in (("src_points_interval", "src_intervals"),
+                     ("src_points_values", "src_values"),
+                     ("rec_points_interval", "rec_intervals"),
+                     ("rec_points_values", "rec_values"),
+                     ("rec_points_values_offset", "rec_offsets")):
+            assert np.array_equal(seen[a], p[b]), (name, a)
+        assert list(seen["boundary_condition"]) == list(p["bc"])
+    short = workloads.api_solver("readme_2d", timesteps=40)
+    assert short.time_model.timesteps in (40, 41)

@@ -96,10 +96,15 @@ def bytes_per_point(p):
 
 
 # ---------------------------------------------------------------------------
-def readme_2d(timesteps=None):
-    """C1: README 2D two-layer model (reference README.md:54-137)."""
+def readme_2d_velocity():
     vel = np.full((513, 513), 1500.0, dtype=np.float32)
     vel[257:] = 2000.0
+    return vel
+
+
+def readme_2d(timesteps=None):
+    """C1: README 2D two-layer model (reference README.md:54-137)."""
+    vel = readme_2d_velocity()
     return _assemble(
         vel, None, ((0, 0), (0, 0)), (10.0, 10.0), 4,
         ("null_neumann", "null_dirichlet", "none", "null_dirichlet"),
@@ -107,8 +112,7 @@ def readme_2d(timesteps=None):
         1, 10.0, 1.0, timesteps, name="readme_2d")
 
 
-def marmousi_2d(space_order=8, timesteps=None, seed=1):
-    """C2: Marmousi-shaped 351 x 1701 model (benchmark/marmousi_2D.py:71-113)."""
+def marmousi_2d_velocity(seed=1):
     nz, nx = 351, 1701
     rng = np.random.default_rng(seed)
     z = np.arange(nz, dtype=np.float64)[:, None]
@@ -121,7 +125,12 @@ def marmousi_2d(space_order=8, timesteps=None, seed=1):
     smooth = np.kron(coarse, np.ones((30, 43)))[:nz, :nx]
     vel = vel * (1.0 + 0.03 * np.tanh(smooth))
     vel[:20] = 1500.0                        # water layer
-    vel = np.clip(vel, 1028.0, 4700.0).astype(np.float32)
+    return np.clip(vel, 1028.0, 4700.0).astype(np.float32)
+
+
+def marmousi_2d(space_order=8, timesteps=None, seed=1):
+    """C2: Marmousi-shaped 351 x 1701 model (benchmark/marmousi_2D.py:71-113)."""
+    vel = marmousi_2d_velocity(seed)
     return _assemble(
         vel, None, ((0, 70), (70, 70)), (10.0, 10.0), space_order,
         ("null_neumann", "null_dirichlet", "null_dirichlet", "null_dirichlet"),
@@ -230,8 +239,9 @@ def reshoot(base, shot):
         shape, to_grid(src), 4, dtype)
     p["rec_intervals"], p["rec_values"], p["rec_offsets"] = _tables(
         shape, to_grid(rec), 4, dtype)
-    p["u"] = np.zeros_like(base["u"])
-    p["receivers"] = np.zeros_like(base["receivers"])
+    # np.zeros maps untouched zero pages; zeros_like would write 1.7 GB per shot
+    p["u"] = np.zeros(base["u"].shape, dtype=base["u"].dtype)
+    p["receivers"] = np.zeros(base["receivers"].shape, dtype=base["receivers"].dtype)
     p["shot"] = shot
     return p
 
@@ -381,6 +391,53 @@ def slab_3d(rank=0, world=1, planes_per_gpu=128, n=1040, space_order=16,
         "slab_up": int(rank > 0), "slab_down": int(rank < world - 1),
         "global_shape": shape, "owned_planes": hi - lo,
     }
+
+
+# ---------------------------------------------------------------------------
+# The same configurations through the public API (SpaceModel, TimeModel,
+# Source, Receiver, RickerWavelet, Solver): what a simwave user writes.  The
+# objects produce the same arrays as the builders above (tests/test_workloads.py).
+_API_SPECS = {
+    # name: (velocity, bounding box, spacing, space_order, damping length, bc,
+    #        tf, source coordinates, receiver coordinates, window radius, f0)
+    "readme_2d": lambda: (
+        readme_2d_velocity(), (0, 5120, 0, 5120), (10., 10.), 4, 0,
+        ("null_neumann", "null_dirichlet", "none", "null_dirichlet"), 1.0,
+        [(2560., 2560.)], [(2560., 10. * i) for i in range(512)], 1, 10.0),
+    "marmousi_2d": lambda: (
+        marmousi_2d_velocity(), (0, 3500, 0, 17000), (10., 10.), 8,
+        (0, 700, 700, 700),
+        ("null_neumann", "null_dirichlet", "null_dirichlet", "null_dirichlet"),
+        2.0, [(20., 8500.)], [(20., 10. * i) for i in range(1700)], 1, 10.0),
+    "overthrust_3d": lambda: (
+        _layered_3d((207, 801, 801), 2179.0, 6000.0, 2),
+        (0, 4120, 0, 16000, 0, 16000), (20., 20., 20.), 8, 0,
+        ("null_neumann", "null_dirichlet", "null_dirichlet", "null_dirichlet",
+         "null_dirichlet", "null_dirichlet"), 4.0,
+        [(20., 8000., 8000.)], [(20., 8000., 20. * i) for i in range(800)], 1, 8.0),
+}
+
+
+def api_solver(name, timesteps=None, compiler=None):
+    """``simwave_b200.Solver`` of workload ``name`` built the way the
+    reference's benchmark scripts build it (benchmark/overthrust_3D.py:77-126,
+    benchmark/marmousi_2D.py:71-126, README.md:54-137).  ``timesteps`` shortens
+    the run (tf is cut accordingly)."""
+    import simwave_b200 as api
+    (vel, box, h, order, damping, bc, tf, src, rec, radius, f0) = _API_SPECS[name]()
+    space = api.SpaceModel(bounding_box=box, grid_spacing=h, velocity_model=vel,
+                           space_order=order, dtype=np.float32)
+    space.config_boundary(damping_length=damping, boundary_condition=bc,
+                          damping_polynomial_degree=3, damping_alpha=0.001)
+    time = api.TimeModel(space_model=space, tf=tf)
+    if timesteps is not None and timesteps < time.timesteps:
+        time = api.TimeModel(space_model=space,
+                             tf=float(time.dt) * (timesteps - 1) * (1 - 1e-6))
+    source = api.Source(space, coordinates=src, window_radius=radius)
+    receiver = api.Receiver(space_model=space, coordinates=rec, window_radius=radius)
+    wavelet = api.RickerWavelet(f0, time)
+    return api.Solver(space_model=space, time_model=time, sources=source,
+                      receivers=receiver, wavelet=wavelet, compiler=compiler)
 
 
 WORKLOADS = {

@@ -215,6 +215,20 @@ void simwave_cuda_last_timing(double *loop, double *h2d, double *d2h,
  * number of values available. */
 int simwave_cuda_last_timing_ex(double *out, int n);
 
+/*
+ * `forward` over several devices of this process (new functionality: the
+ * reference is single-device).  A 3D problem with
+ * saving_stride == 0 is cut into z-slabs, one per listed device, each with its
+ * own host thread inside the call; ghost planes travel device to device over
+ * NVLink (peer stores fused into the step kernel, device-side step flags);
+ * every slab copies the planes it owns back into the caller's `u`, traces are
+ * summed over slabs.  The wavefield is bit-identical to the single-device run.
+ * Also selectable without code: SIMWAVE_CUDA_NGPUS=<n> (devices base .. base +
+ * n - 1, base = SIMWAVE_CUDA_DEVICE or 0) or SIMWAVE_CUDA_DEVICES=<d0,d1,..>.
+ * count == 0 returns this thread to the environment's setting.
+ */
+int simwave_cuda_set_slab_devices(const int *devices, int count);
+
 /* Number of kernels launched by the last forward()/plan run on this thread. */
 unsigned long long simwave_cuda_last_launch_count(void);
 
@@ -306,6 +320,12 @@ typedef struct simwave_problem {
      * refreshes them every step from the neighbour's device over NVLink.
      * Needs saving_stride == 0 and a connected plan (below). */
     int slab_up, slab_down;
+    /* A slab whose host arrays are windows of larger ones (0 = dense): distance
+     * in elements between consecutive slots of `u`, and the range of local
+     * planes [out_plane_begin, out_plane_end) that simwave_plan_download()
+     * writes back (0, 0 = all of them).  Used by the multi-device `forward`. */
+    size_t u_slot_stride;
+    size_t out_plane_begin, out_plane_end;
 } simwave_problem;
 
 simwave_plan *simwave_plan_create(const simwave_problem *problem);

@@ -1,8 +1,14 @@
 // extern "C" surface of libsimwave_b200.so (declared in include/simwave_cuda.h)
+#include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #include "sw_engine.h"
 
@@ -29,10 +35,287 @@ static Options current_options()
     return o;
 }
 
+// ---------------------------------------------------------------------------
+// `forward` on several devices of one process: slab decomposition along z.
+//
+// The caller's arrays are cut into contiguous z-ranges, one per device (plane
+// = nx*ny contiguous elements, so a slab of the model is a pointer offset, no
+// copy); every slab gets a plan with r ghost planes per inner face, its own
+// host thread, and its neighbours' device pointers (peer access, no IPC).  The
+// time loop is the one of the multi-process form (sw_engine.cu: fused peer
+// stores + device-side step flags).  Each slab copies the planes it owns
+// straight back into the caller's `u`; receiver traces are partial sums,
+// added in slab order.  Selected with SIMWAVE_CUDA_NGPUS=<n> (devices base,
+// base+1, ... where base = SIMWAVE_CUDA_DEVICE or 0), SIMWAVE_CUDA_DEVICES=
+// <comma list>, or simwave_cuda_set_slab_devices(); 3D, saving_stride == 0.
+// ---------------------------------------------------------------------------
+static thread_local std::vector<int> g_slabDevices;
+
+static std::vector<int> slab_devices()
+{
+    if (!g_slabDevices.empty())
+        return g_slabDevices;
+    std::vector<int> out;
+    if (const char *list = std::getenv("SIMWAVE_CUDA_DEVICES")) {
+        for (const char *p = list; *p;) {
+            char *endp = nullptr;
+            const long v = std::strtol(p, &endp, 10);
+            if (endp == p)
+                break;
+            out.push_back((int)v);
+            p = (*endp == ',') ? endp + 1 : endp;
+        }
+        return out;
+    }
+    if (const char *n = std::getenv("SIMWAVE_CUDA_NGPUS")) {
+        const int count = std::atoi(n);
+        int base = g_deviceOverride >= 0 ? g_deviceOverride : 0;
+        if (g_deviceOverride < 0)
+            if (const char *d = std::getenv("SIMWAVE_CUDA_DEVICE"))
+                base = std::atoi(d);
+        for (int k = 0; k < count; k++)
+            out.push_back(base + k);
+    }
+    return out;
+}
+
+namespace {
+// rendezvous of the slab threads; a thread that fails leaves for good
+class Rendezvous {
+public:
+    explicit Rendezvous(int n) : expected_(n) {}
+    // false: somebody failed, give up
+    bool meet()
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (failed_)
+            return false;
+        const unsigned long long gen = generation_;
+        if (++waiting_ == expected_) {
+            waiting_ = 0;
+            generation_++;
+            cv_.notify_all();
+        } else {
+            cv_.wait(lk, [&] { return generation_ != gen || failed_; });
+        }
+        return !failed_;
+    }
+    void fail(const std::string &why)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!failed_)
+            error_ = why;
+        failed_ = true;
+        cv_.notify_all();
+    }
+    bool failed() { std::lock_guard<std::mutex> lk(mu_); return failed_; }
+    std::string error() { std::lock_guard<std::mutex> lk(mu_); return error_; }
+private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    int expected_, waiting_ = 0;
+    unsigned long long generation_ = 0;
+    bool failed_ = false;
+    std::string error_;
+};
+
+// Clip every window's z-interval to the planes [zLo, zHi) a slab answers for
+// and shift it to local plane indices; a window that lies elsewhere becomes
+// one zero-weight point (same as simwave_b200/slab.py:_clip_tables).
+struct ClippedTables {
+    std::vector<size_t> intervals, offsets;
+    std::vector<unsigned char> values;   // element size = dtype_bytes
+};
+ClippedTables clip_tables(const size_t *iv, const void *values, const size_t *offsets,
+                          size_t count, int elem, size_t zLo, size_t zHi, size_t zShift)
+{
+    ClippedTables t;
+    t.intervals.assign(iv, iv + count * 6);
+    t.offsets.assign(1, 0);
+    const unsigned char *v = (const unsigned char *)values;
+    for (size_t i = 0; i < count; i++) {
+        const size_t zb = iv[i * 6], ze = iv[i * 6 + 1];
+        const size_t total = offsets[i + 1] - offsets[i];
+        const size_t nzw = ze - zb + 1;
+        const unsigned char *wz = v + offsets[i] * elem;
+        const unsigned char *rest = wz + nzw * elem;
+        const size_t restCount = total - nzw;
+        size_t cb = std::max(zb, zLo), ce = std::min(ze, zHi - 1);
+        size_t kept = 0;
+        if (cb > ce || ze < zLo) {
+            cb = ce = std::min(std::max(zb, zLo), zHi - 1);
+            t.values.insert(t.values.end(), (size_t)elem, 0);     // one zero weight
+            kept = 1;
+        } else {
+            t.values.insert(t.values.end(), wz + (cb - zb) * elem, wz + (ce - zb + 1) * elem);
+            kept = ce - cb + 1;
+        }
+        t.values.insert(t.values.end(), rest, rest + restCount * elem);
+        t.intervals[i * 6] = cb - zShift;
+        t.intervals[i * 6 + 1] = ce - zShift;
+        t.offsets.push_back(t.offsets.back() + kept + restCount);
+    }
+    if (t.values.empty())
+        t.values.resize((size_t)elem, 0);
+    return t;
+}
+}  // namespace
+
+static double run_forward_slabs(const simwave_problem &pb, size_t begin, size_t end,
+                                const std::vector<int> &devices)
+{
+    const double t0 = wall();
+    const int world = (int)devices.size();
+    const size_t r = pb.space_order / 2;
+    const size_t nz = pb.nz, plane = pb.nx * pb.ny;
+    const size_t interior = nz - 2 * r;
+    const int elem = pb.dtype_bytes;
+    if (interior / world < 2 * r)
+        throw Error("too many devices for " + std::to_string(interior) + " interior planes");
+    int have = 0;
+    SW_CUDA(cudaGetDeviceCount(&have));
+    for (int d : devices)
+        if (d < 0 || d >= have)
+            throw Error("slab device ordinal " + std::to_string(d) + " out of range");
+
+    // owned interior ranges, as even as possible (slab.py:split_planes)
+    std::vector<size_t> lo(world), hi(world);
+    {
+        const size_t base = interior / world, extra = interior % world;
+        size_t at = r;
+        for (int k = 0; k < world; k++) {
+            lo[k] = at;
+            at += base + ((size_t)k < extra ? 1 : 0);
+            hi[k] = at;
+        }
+    }
+    const size_t rows = pb.wavelet_size;
+    std::vector<std::vector<unsigned char>> traces(world);
+    std::vector<SlabPeer> peers(world);
+    std::vector<Timing> timings(world);
+    Rendezvous meet(world);
+    const Options base = current_options();
+
+    auto slab_thread = [&](int k) {
+        try {
+            Options opt = base;
+            opt.device = devices[k];
+            const size_t a = lo[k] - r, b = hi[k] + r;
+            const bool up = k > 0, down = k < world - 1;
+            const size_t ownLo = up ? lo[k] : 0, ownHi = down ? hi[k] : nz;
+            simwave_problem q = pb;
+            auto shifted = [&](const void *p) {
+                return p ? (const void *)((const char *)p + a * plane * elem) : nullptr;
+            };
+            q.u = (void *)shifted(pb.u);
+            q.velocity = shifted(pb.velocity);
+            q.density = shifted(pb.density);
+            q.damp = shifted(pb.damp);
+            q.nz = b - a;
+            q.u_slot_stride = nz * plane;
+            q.out_plane_begin = ownLo - a;
+            q.out_plane_end = ownHi - a;
+            q.slab_up = up;
+            q.slab_down = down;
+            size_t bc[6];
+            for (int i = 0; i < 6; i++) bc[i] = pb.boundary_conditions[i];
+            if (up) bc[0] = 0;
+            if (down) bc[1] = 0;
+            q.boundary_conditions = bc;
+            const ClippedTables src =
+                clip_tables(pb.src_points_interval, pb.src_points_values,
+                            pb.src_points_values_offset, pb.num_sources, elem, ownLo, ownHi, a);
+            const ClippedTables rec =
+                clip_tables(pb.rec_points_interval, pb.rec_points_values,
+                            pb.rec_points_values_offset, pb.num_receivers, elem, ownLo, ownHi, a);
+            q.src_points_interval = src.intervals.data();
+            q.src_points_values = src.values.data();
+            q.src_points_values_size = src.values.size() / elem;
+            q.src_points_values_offset = src.offsets.data();
+            q.rec_points_interval = rec.intervals.data();
+            q.rec_points_values = rec.values.data();
+            q.rec_points_values_size = rec.values.size() / elem;
+            q.rec_points_values_offset = rec.offsets.data();
+            traces[k].assign(std::max<size_t>(1, rows * pb.num_receivers) * elem, 0);
+            q.receivers = traces[k].data();
+
+            std::unique_ptr<PlanBase> plan = make_plan(q, opt);
+            plan->slab_peer(&peers[k]);
+            if (!meet.meet())
+                return;
+            plan->slab_connect_direct(up ? &peers[k - 1] : nullptr,
+                                      down ? &peers[k + 1] : nullptr);
+            if (!meet.meet())
+                return;
+            if (begin <= end)
+                plan->run(begin, end);
+            plan->download(nullptr, nullptr);
+            timings[k] = plan->timing;
+            // the neighbours' kernels store into my ghost planes until THEIR
+            // loops end: nobody frees anything before everybody is done
+            meet.meet();
+        } catch (const std::exception &e) {
+            meet.fail("slab " + std::to_string(k) + " (device " + std::to_string(devices[k]) +
+                      "): " + e.what());
+        } catch (...) {
+            meet.fail("slab " + std::to_string(k) + ": unknown failure");
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int k = 0; k < world; k++)
+        threads.emplace_back(slab_thread, k);
+    for (auto &t : threads)
+        t.join();
+    if (meet.failed())
+        throw Error(meet.error());
+
+    // traces: partial sums of the slabs, added in slab order
+    if (pb.receivers && pb.num_receivers && begin <= end) {
+        const size_t first = (begin - 1) * pb.num_receivers;
+        const size_t count = (end - begin + 1) * pb.num_receivers;
+        if (elem == 4) {
+            float *out = (float *)pb.receivers + first;
+            for (size_t i = 0; i < count; i++) {
+                float s = ((const float *)traces[0].data())[first + i];
+                for (int k = 1; k < world; k++)
+                    s += ((const float *)traces[k].data())[first + i];
+                out[i] = s;
+            }
+        } else {
+            double *out = (double *)pb.receivers + first;
+            for (size_t i = 0; i < count; i++) {
+                double s = ((const double *)traces[0].data())[first + i];
+                for (int k = 1; k < world; k++)
+                    s += ((const double *)traces[k].data())[first + i];
+                out[i] = s;
+            }
+        }
+    }
+    Timing t;
+    for (const Timing &x : timings) {
+        t.loop = std::max(t.loop, x.loop);
+        t.h2d = std::max(t.h2d, x.h2d);
+        t.d2h = std::max(t.d2h, x.d2h);
+        t.run_wall = std::max(t.run_wall, x.run_wall);
+        t.launches += x.launches;
+    }
+    t.total = wall() - t0;
+    last_timing() = t;
+    if (std::getenv("SIMWAVE_CUDA_VERBOSE"))
+        std::fprintf(stderr,
+                     "simwave_b200: forward on %d devices %.3f s = upload %.3f + run %.3f "
+                     "(device loop %.3f) + download %.3f (max over slabs)\n",
+                     world, t.total, t.h2d, t.run_wall, t.loop, t.d2h);
+    return t.total;
+}
+
 // The whole of `forward`: upload, time loop, drain.
 static double run_forward(const simwave_problem &pb, size_t begin, size_t end)
 {
     try {
+        const std::vector<int> devices = slab_devices();
+        if (devices.size() > 1 && pb.ndim == 3 && pb.saving_stride == 0)
+            return run_forward_slabs(pb, begin, end, devices);
         const double t0 = wall();
         std::unique_ptr<PlanBase> plan = make_plan(pb, current_options());
         if (begin <= end)
@@ -107,6 +390,16 @@ int simwave_cuda_last_timing_ex(double *out, int n)
     for (int i = 0; i < n && i < 6; i++)
         out[i] = v[i];
     return 6;
+}
+
+int simwave_cuda_set_slab_devices(const int *devices, int count)
+{
+    if (count < 0 || (count > 0 && !devices)) {
+        sw::set_last_error("simwave_cuda_set_slab_devices: bad arguments");
+        return -1;
+    }
+    sw::g_slabDevices.assign(devices, devices + count);
+    return 0;
 }
 
 void simwave_cuda_release_cache(void)

@@ -458,7 +458,8 @@ constexpr unsigned kSlabMagic = 0x534c4142u;   // "SLAB"
 
 // flags[0]: last step whose halo the UP neighbour has delivered, [1]: same for
 // DOWN, [2]: error word (1 = timed out)
-__global__ void slab_wait_kernel(int *flags, int needUp, int needDown, int value)
+__global__ void slab_wait_kernel(int *flags, int needUp, int needDown, int value,
+                                 long long timeoutCycles)
 {
     const long long start = clock64();
     for (int side = 0; side < 2; side++) {
@@ -470,7 +471,7 @@ __global__ void slab_wait_kernel(int *flags, int needUp, int needDown, int value
                          : "memory");
             if (v >= value)
                 break;
-            if (clock64() - start > 40000000000LL) {   // ~20 s: neighbour is gone
+            if (clock64() - start > timeoutCycles) {   // neighbour is gone
                 flags[2] = 1;
                 return;
             }
@@ -559,6 +560,8 @@ public:
     void reset() override;
     void slab_export(void *desc) override;
     void slab_connect(const void *up, const void *down) override;
+    void slab_peer(SlabPeer *out) override;
+    void slab_connect_direct(const SlabPeer *up, const SlabPeer *down) override;
 
 private:
     using StepFn = void (*)(int, const StepArgs<T> &, cudaStream_t);
@@ -586,6 +589,8 @@ private:
     Grid g_;
     size_t guard_;          // elements before/after each field allocation
     size_t denseCells_;
+    size_t hostSlotStride_;            // elements between slots of the caller's u
+    size_t outPlaneLo_ = 0, outPlaneHi_ = 0;   // local planes download() writes back
     size_t fieldBytes_;
 
     T *hostU_;
@@ -649,6 +654,7 @@ private:
     int peerNS_[2] = {0, 0};
     std::vector<void *> ipcMapped_;
     bool slabFused_ = false;   // ghost copies written by the step / source kernels themselves
+    size_t ranLo_ = 0, ranHi_ = 0;   // contiguous range of steps run since the last reset (0: none)
     void slab_wait(size_t n);
     void slab_push(size_t n, size_t slot);
 };
@@ -700,6 +706,15 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     g.cells = (long long)g.nS * g.planeStride;
     guard_ = 2 * align;
     denseCells_ = (size_t)g.nS * g.nM * g.nF;
+    hostSlotStride_ = pb.u_slot_stride ? pb.u_slot_stride : denseCells_;
+    outPlaneLo_ = 0;
+    outPlaneHi_ = (size_t)g.nS;
+    if (pb.out_plane_end > pb.out_plane_begin) {
+        if (pb.out_plane_end > (size_t)g.nS)
+            throw Error("out_plane range outside the slab");
+        outPlaneLo_ = pb.out_plane_begin;
+        outPlaneHi_ = pb.out_plane_end;
+    }
     fieldBytes_ = (g.cells + 2 * guard_) * sizeof(T);
 
     hostU_ = (T *)pb.u;
@@ -720,11 +735,12 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     std::future<void> zeroScan;
     if (!opt_.zeroIn && !(numSlots_ == 3 && is_pinned_host(hostU_)))
         zeroScan = std::async(std::launch::async, [this] {
-            if (all_zero(hostU_, numSlots_ * denseCells_ * sizeof(T))) {
+            if (hostSlotStride_ == denseCells_ &&
+                all_zero(hostU_, numSlots_ * denseCells_ * sizeof(T))) {
                 std::fill(slotZero_.begin(), slotZero_.end(), 1);
             } else {
                 for (size_t s = 0; s < numSlots_; s++)
-                    slotZero_[s] = all_zero(hostU_ + s * denseCells_, denseCells_ * sizeof(T));
+                    slotZero_[s] = all_zero(hostU_ + s * hostSlotStride_, denseCells_ * sizeof(T));
             }
         });
     slabUp_ = pb.slab_up != 0;
@@ -1057,7 +1073,7 @@ void Plan<T>::ensure_live(size_t slot)
     // whole allocation (guards and row padding included) starts from zero
     SW_CUDA(cudaMemsetAsync((char *)(buf - g_.lpad - guard_), 0, fieldBytes_, stream_));
     if (!slotZero_[slot])
-        upload_dense(hostU_ + slot * denseCells_, buf);
+        upload_dense(hostU_ + slot * hostSlotStride_, buf);
     live_[slot] = buf;
     dirty_[slot] = false;
 }
@@ -1079,11 +1095,11 @@ void Plan<T>::retire(size_t slot, bool keep)
         return;
     }
     HostDrain::Job job;
-    job.src = buf;
-    job.dst = hostU_ + slot * denseCells_;
+    job.src = buf + (long long)outPlaneLo_ * g_.planeStride;
+    job.dst = hostU_ + slot * hostSlotStride_ + outPlaneLo_ * (size_t)g_.nM * g_.nF;
     job.rowBytes = (size_t)g_.nF * sizeof(T);
     job.srcPitchBytes = (size_t)g_.pitch * sizeof(T);
-    job.rows = (size_t)g_.nS * g_.nM;
+    job.rows = (outPlaneHi_ - outPlaneLo_) * (size_t)g_.nM;
     SW_CUDA(cudaEventCreateWithFlags(&job.ready, cudaEventDisableTiming));
     SW_CUDA(cudaEventRecord(job.ready, stream_));
     if (!keep)
@@ -1394,8 +1410,14 @@ void Plan<T>::run(size_t begin, size_t end)
                             (long long)(g_.nS - 2 * g_.r) * g_.planeStride;
         }
 
-        if (slabUp_ || slabDown_)
+        // the halo of step n-1 arrives only if that step ran since the last
+        // reset (all slabs run the same ranges); the first step of a fresh
+        // range reads the ghost planes that were uploaded
+        if ((slabUp_ || slabDown_) && ranHi_ != 0 && n - 1 >= ranLo_ && n - 1 <= ranHi_)
             slab_wait(n);
+        if (ranHi_ == 0 || n != ranHi_ + 1)
+            ranLo_ = n;
+        ranHi_ = n;
         stepNow_ = n;
         launch_receivers(a.cur, n);
         launch_step(a);
@@ -1547,7 +1569,7 @@ void Plan<T>::reset()
             T *buf = live_.at(s);
             SW_CUDA(cudaMemsetAsync((char *)(buf - g_.lpad - guard_), 0, fieldBytes_, stream_));
             if (!slotZero_[s])
-                upload_dense(hostU_ + s * denseCells_, buf);
+                upload_dense(hostU_ + s * hostSlotStride_, buf);
             dirty_[s] = false;
         }
         SW_CUDA(cudaMemsetAsync(slabFlags_.get(), 0, slabFlags_.bytes(), stream_));
@@ -1559,6 +1581,7 @@ void Plan<T>::reset()
     }
     prevT_ = 0; curT_ = 1; nextT_ = 2;
     recBegin_ = recEnd_ = 0;
+    ranLo_ = ranHi_ = 0;
     SW_CUDA(cudaMemsetAsync(recOut_.get(), 0, recOut_.bytes(), stream_));
     timing.launches = 0;
     SW_CUDA(cudaStreamSynchronize(stream_));
@@ -1617,13 +1640,72 @@ void Plan<T>::slab_connect(const void *up, const void *down)
                  !env_is("SIMWAVE_CUDA_SLAB_PUSH", "copy");
 }
 
+template <typename T>
+void Plan<T>::slab_peer(SlabPeer *out)
+{
+    if (!(slabUp_ || slabDown_))
+        throw Error("not a slab plan");
+    for (size_t s = 0; s < 3; s++)
+        out->slot[s] = live_.at(s);
+    out->flags = slabFlags_.as<int>();
+    out->nS = g_.nS; out->nM = g_.nM; out->nF = g_.nF; out->r = g_.r; out->lpad = g_.lpad;
+    out->pitch = g_.pitch;
+    out->device = device_;
+    out->dtypeBytes = (int)sizeof(T);
+}
+
+// Neighbours living in the same process (one plan per device, one host thread
+// each): peer access instead of IPC mappings, otherwise the same protocol.
+template <typename T>
+void Plan<T>::slab_connect_direct(const SlabPeer *up, const SlabPeer *down)
+{
+    if ((slabUp_ && !up) || (slabDown_ && !down))
+        throw Error("slab_connect_direct: missing neighbour");
+    const SlabPeer *peers[2] = {slabUp_ ? up : nullptr, slabDown_ ? down : nullptr};
+    for (int side = 0; side < 2; side++) {
+        const SlabPeer *d = peers[side];
+        if (!d)
+            continue;
+        if (d->dtypeBytes != (int)sizeof(T) || d->nM != g_.nM || d->nF != g_.nF ||
+            d->r != g_.r || d->pitch != g_.pitch || d->lpad != g_.lpad)
+            throw Error("slab_connect_direct: neighbour slab has a different plane layout");
+        if (d->device != device_) {
+            int can = 0;
+            SW_CUDA(cudaDeviceCanAccessPeer(&can, device_, d->device));
+            if (!can)
+                throw Error("device " + std::to_string(device_) + " cannot access device " +
+                            std::to_string(d->device) + " (no peer path)");
+            cudaError_t e = cudaDeviceEnablePeerAccess(d->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                throw Error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        for (int s = 0; s < 3; s++)
+            peerSlot_[side][s] = (T *)d->slot[s];
+        peerFlags_[side] = d->flags + (side == 0 ? 1 : 0);
+        peerNS_[side] = d->nS;
+    }
+    slabConnected_ = true;
+    slabFused_ = args_.fuse_bc && srcMode_ != SRC_ATOMIC &&
+                 !env_is("SIMWAVE_CUDA_SLAB_PUSH", "copy");
+}
+
 // before step n reads the ghost planes of u_cur: the neighbours must have
 // delivered the halo they produced in step n-1
 template <typename T>
 void Plan<T>::slab_wait(size_t n)
 {
+    // SIMWAVE_CUDA_SLAB_TIMEOUT: seconds a step waits for its neighbours'
+    // halos before the run is declared broken (default 20; ranks that start
+    // with more skew than that need a larger value)
+    static const double seconds = [] {
+        const char *e = std::getenv("SIMWAVE_CUDA_SLAB_TIMEOUT");
+        const double v = e ? std::atof(e) : 0.0;
+        return v > 0 ? v : 20.0;
+    }();
     slab_wait_kernel<<<1, 1, 0, stream_>>>(slabFlags_.as<int>(), slabUp_ ? 1 : 0,
-                                           slabDown_ ? 1 : 0, (int)n - 1);
+                                           slabDown_ ? 1 : 0, (int)n - 1,
+                                           (long long)(seconds * 2.0e9));
     check_launch("slab_wait_kernel");
 }
 

@@ -120,6 +120,15 @@ private:
     std::string error_;
 };
 
+// What a slab plan shows its neighbours inside one process (the single-process
+// multi-device `forward`): raw device pointers instead of CUDA IPC handles.
+struct SlabPeer {
+    void *slot[3] = {nullptr, nullptr, nullptr};   // element (0,0,0) of each wavefield slot
+    int *flags = nullptr;                          // {from up, from down, error}
+    int nS = 0, nM = 0, nF = 0, r = 0, lpad = 0, device = -1, dtypeBytes = 0;
+    long long pitch = 0;
+};
+
 class PlanBase {
 public:
     virtual ~PlanBase() {}
@@ -128,6 +137,8 @@ public:
     virtual void reset() = 0;
     virtual void slab_export(void *desc) = 0;
     virtual void slab_connect(const void *up, const void *down) = 0;
+    virtual void slab_peer(SlabPeer *out) = 0;
+    virtual void slab_connect_direct(const SlabPeer *up, const SlabPeer *down) = 0;
     Timing timing;
 };
 

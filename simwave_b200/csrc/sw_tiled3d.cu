@@ -1,5 +1,7 @@
 // Host side of the tiled 3D kernel: configuration table and launch.
 // Compiled once per radius (-DSW_RADIUS=1..10) so the build parallelises.
+#include <atomic>
+
 #include "sw_launch.h"
 #include "sw_step_tiled3d.cuh"
 
@@ -24,15 +26,16 @@ static void launch_cfg(int math, const StepArgs<float> &a, const StepMaps &maps,
     auto kStrict = step3d_tiled_kernel<R, PM, TX, TY, PF, PS, MATH_STRICT, MINB, VARDEN, UNR>;
     auto kFast = step3d_tiled_kernel<R, PM, TX, TY, PF, PS, MATH_FAST, MINB, VARDEN, UNR>;
     auto k = (math == MATH_STRICT) ? kStrict : kFast;
-    // the shared-memory opt-in is per device: one bit per ordinal
-    static unsigned long long configured[2] = {0, 0};
+    // the shared-memory opt-in is per device: one bit per ordinal (atomic: one
+    // host thread per device may be launching, simwave_cuda_set_slab_devices)
+    static std::atomic<unsigned long long> configured[2];
     int dev = 0;
     SW_CUDA(cudaGetDevice(&dev));
-    unsigned long long &mask = configured[math == MATH_STRICT];
-    if (!(mask >> (dev & 63) & 1ull)) {
+    std::atomic<unsigned long long> &mask = configured[math == MATH_STRICT];
+    if (!(mask.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
         SW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      smemBytes));
-        mask |= 1ull << (dev & 63);
+        mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     k<<<grid, TL::THREADS, smemBytes, stream>>>(a, maps, qflags, zChunk);
 }

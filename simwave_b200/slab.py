@@ -153,6 +153,8 @@ class _Problem(ctypes.Structure):
         ("saving_stride", ctypes.c_size_t), ("dt", ctypes.c_double),
         ("space_order", ctypes.c_size_t), ("num_snapshots", ctypes.c_size_t),
         ("slab_up", ctypes.c_int), ("slab_down", ctypes.c_int),
+        ("u_slot_stride", ctypes.c_size_t),
+        ("out_plane_begin", ctypes.c_size_t), ("out_plane_end", ctypes.c_size_t),
     ]
 
 

@@ -104,3 +104,42 @@ def test_slabs_on_one_device_equal_the_single_plan_run(shape, order, density, st
     oracle.forward(cpu)
     assert rel_l2(u, cpu["u"]) <= 1e-5
     assert rel_l2(traces, cpu["receivers"]) <= 1e-5
+
+
+def _device_count():
+    from cuda_abi import core
+    return core().simwave_cuda_device_count()
+
+
+@pytest.mark.parametrize("math", ["strict", "fast"])
+@pytest.mark.parametrize("shape,order,density,steps,bc,world", CASES)
+def test_forward_over_several_devices_of_one_process(shape, order, density, steps, bc, world,
+                                                     math, monkeypatch):
+    """SIMWAVE_CUDA_NGPUS: the drop-in forward() itself cuts the problem into
+    slabs, one device and one host thread each (no torchrun, no user-side
+    reduction).  Needs as many GPUs as slabs; the wavefield must be
+    bit-identical to the single-device call, the traces agree to rounding."""
+    if _device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    monkeypatch.setenv("SIMWAVE_CUDA_MATH", math)
+    r = order // 2
+    cuts = [lo for lo, _ in slab.split_planes(shape[0], r, world)][1:]
+    p = problems.make_problem(**problem_kwargs(shape, order, density, steps, bc, cuts))
+    single = problems.clone(p)
+    cuda_forward(single)
+    monkeypatch.setenv("SIMWAVE_CUDA_NGPUS", str(world))
+    multi = problems.clone(p)
+    cuda_forward(multi)
+    assert np.abs(single["u"]).max() > 0
+    assert np.array_equal(multi["u"], single["u"])
+    assert rel_l2(multi["receivers"], single["receivers"]) <= 2e-6
+    # through the public API as well: nothing but the environment changes
+    multi2 = problems.clone(p)
+    multi2["begin_timestep"], multi2["end_timestep"] = 1, steps - 3
+    part = problems.clone(p)
+    part["end_timestep"] = steps - 3
+    monkeypatch.delenv("SIMWAVE_CUDA_NGPUS")
+    cuda_forward(part)
+    monkeypatch.setenv("SIMWAVE_CUDA_DEVICES", ",".join(str(d) for d in range(world)))
+    cuda_forward(multi2)
+    assert np.array_equal(multi2["u"], part["u"])

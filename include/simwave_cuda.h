@@ -184,6 +184,158 @@ double simwave_cuda_forward_3d_variable_f64(
     size_t space_order, size_t num_snapshots);
 
 /* ------------------------------------------------------------------------
+ * 1b. adjoint operator (constant density)
+ *
+ * New: the reference ships only `forward`; its source tree and Middleware are
+ * laid out per operator (simwave/kernel/backend/compiler.py:145-147
+ * c_code/<operator>/..., middleware.py:103-104), and an `adjoint` is what an
+ * FWI user needs next.  Same argument lists as the
+ * forward entry points above (constant_density/{2,3}d/wave.c:23-36), with the
+ * roles of two arrays exchanged:
+ *     receivers [wavelet_size][num_receivers]  INPUT: the data d
+ *     wavelet   [wavelet_size][wavelet_count]  OUTPUT: g = F^T d, where F is the
+ *               linear map wavelet -> receivers of `forward` started from a
+ *               zero wavefield over [begin_timestep, end_timestep] (rows
+ *               outside that range are left untouched; wavelet_count == 1 gives
+ *               the sum over sources, the transpose of one shared wavelet)
+ *     u         in/out like `forward`: must be zero on entry; returns the last
+ *               three adjoint wavefields (scaled by dt^2 v^2 / D)
+ * Exact transpose (float64: <F w, d> = <w, F^T d> to rounding) for source and
+ * receiver windows among the interior points, every boundary-condition mix and
+ * damping layers; windows reaching into the halo are clipped to the interior.
+ * The variable-density variants exist and return -1 ("constant density only").
+ * The shims export them as `adjoint`, next to `forward`.
+ * ---------------------------------------------------------------------- */
+double simwave_cuda_adjoint_2d_constant_f32(
+    float *u, float *velocity, float *damp,
+    float *wavelet, size_t wavelet_size, size_t wavelet_count,
+    float *coeff, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    float *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    float *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    float *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, float dz, float dx,
+    size_t saving_stride, float dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+double simwave_cuda_adjoint_2d_constant_f64(
+    double *u, double *velocity, double *damp,
+    double *wavelet, size_t wavelet_size, size_t wavelet_count,
+    double *coeff, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    double *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    double *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    double *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, double dz, double dx,
+    size_t saving_stride, double dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+double simwave_cuda_adjoint_3d_constant_f32(
+    float *u, float *velocity, float *damp,
+    float *wavelet, size_t wavelet_size, size_t wavelet_count,
+    float *coeff, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    float *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    float *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    float *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, size_t ny, float dz, float dx, float dy,
+    size_t saving_stride, float dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+double simwave_cuda_adjoint_3d_constant_f64(
+    double *u, double *velocity, double *damp,
+    double *wavelet, size_t wavelet_size, size_t wavelet_count,
+    double *coeff, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    double *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    double *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    double *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, size_t ny, double dz, double dx, double dy,
+    size_t saving_stride, double dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+/* variable-density adjoint: declared for the shims, always refused (-1) */
+double simwave_cuda_adjoint_2d_variable_f32(
+    float *u, float *velocity, float *density, float *damp,
+    float *wavelet, size_t wavelet_size, size_t wavelet_count,
+    float *coeff_order2, float *coeff_order1, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    float *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    float *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    float *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, float dz, float dx,
+    size_t saving_stride, float dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+double simwave_cuda_adjoint_2d_variable_f64(
+    double *u, double *velocity, double *density, double *damp,
+    double *wavelet, size_t wavelet_size, size_t wavelet_count,
+    double *coeff_order2, double *coeff_order1, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    double *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    double *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    double *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, double dz, double dx,
+    size_t saving_stride, double dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+double simwave_cuda_adjoint_3d_variable_f32(
+    float *u, float *velocity, float *density, float *damp,
+    float *wavelet, size_t wavelet_size, size_t wavelet_count,
+    float *coeff_order2, float *coeff_order1, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    float *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    float *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    float *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, size_t ny, float dz, float dx, float dy,
+    size_t saving_stride, float dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+double simwave_cuda_adjoint_3d_variable_f64(
+    double *u, double *velocity, double *density, double *damp,
+    double *wavelet, size_t wavelet_size, size_t wavelet_count,
+    double *coeff_order2, double *coeff_order1, size_t *boundary_conditions,
+    size_t *src_points_interval, size_t src_points_interval_size,
+    double *src_points_values, size_t src_points_values_size,
+    size_t *src_points_values_offset,
+    size_t *rec_points_interval, size_t rec_points_interval_size,
+    double *rec_points_values, size_t rec_points_values_size,
+    size_t *rec_points_values_offset,
+    double *receivers, size_t num_sources, size_t num_receivers,
+    size_t nz, size_t nx, size_t ny, double dz, double dx, double dy,
+    size_t saving_stride, double dt,
+    size_t begin_timestep, size_t end_timestep,
+    size_t space_order, size_t num_snapshots);
+
+/* ------------------------------------------------------------------------
  * 2. side exports
  * ---------------------------------------------------------------------- */
 

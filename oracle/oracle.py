@@ -124,3 +124,78 @@ def forward(p, kind=None, variant=""):
     fn = load(kind, p["velocity"].ndim, p.get("density") is not None,
               p["velocity"].dtype, variant)
     return fn(*abi_args(p))
+
+
+# ---------------------------------------------------------------------------
+# Adjoint operator (test infrastructure, like everything in this module).
+#
+# The reference has no adjoint kernel to compile, so this checker restates the
+# operator the product defines (include/simwave_cuda.h section 1b) with the
+# reference's own forward kernel as its engine: g = F^T d equals the forward
+# run with the tables exchanged -- the traces injected at the receiver windows,
+# the field sampled at the source windows -- and time reversed, with the
+# per-axis weights of a point on a Neumann face plane doubled on the injection
+# side and halved on the sampling side, windows clipped to interior points.
+# Pinned by the one property that defines an adjoint: <F w, d> = <w, F^T d>
+# for random w, d (tests/test_adjoint.py, float64, <= 1e-10), with F the
+# compiled reference.
+# ---------------------------------------------------------------------------
+def adjoint_tables(p, intervals, values, offsets, inject):
+    ndim = p["velocity"].ndim
+    shape = p["velocity"].shape
+    r = p["space_order"] // 2
+    bc = [int(b) for b in p["bc"]]
+    count = len(offsets) - 1
+    iv = np.asarray(intervals).reshape(count, 2 * ndim).copy()
+    out_values, out_offsets = [], [0]
+    for i in range(count):
+        v = values[int(offsets[i]):int(offsets[i + 1])]
+        pos, kept = 0, 0
+        for ax in range(ndim):
+            b, e = int(iv[i, 2 * ax]), int(iv[i, 2 * ax + 1])
+            w = v[pos:pos + e - b + 1]
+            pos += e - b + 1
+            lo, hi = r, shape[ax] - r - 1
+            cb, ce = max(b, lo), min(e, hi)
+            if cb > ce:
+                cb = ce = min(max(b, lo), hi)
+                w = np.zeros(1, dtype=values.dtype)
+            else:
+                w = w[cb - b:ce - b + 1].copy()
+                for face, plane in ((2 * ax, lo), (2 * ax + 1, hi)):
+                    if bc[face] == 2 and cb <= plane <= ce:
+                        w[plane - cb] *= values.dtype.type(2.0 if inject else 0.5)
+            iv[i, 2 * ax], iv[i, 2 * ax + 1] = cb, ce
+            out_values.append(w)
+            kept += w.size
+        out_offsets.append(out_offsets[-1] + kept)
+    return (np.ascontiguousarray(iv.reshape(-1).astype(np.uint64)),
+            np.ascontiguousarray(np.concatenate(out_values).astype(values.dtype)),
+            np.asarray(out_offsets, dtype=np.uint64))
+
+
+def adjoint(p, kind=None, variant=""):
+    """g = F^T d for problem dict ``p``: reads p['receivers'] (the data d),
+    writes p['wavelet'] (rows begin-1 .. end-1) and p['u'] in place, like the
+    product's `adjoint` entry points."""
+    if p.get("density") is not None:
+        raise ValueError("adjoint: constant density only")
+    begin, end = p.get("begin_timestep", 1), p["end_timestep"]
+    steps = end - begin + 1
+    nsrc, nrec = len(p["src_offsets"]) - 1, len(p["rec_offsets"]) - 1
+    q = dict(p)
+    q["src_intervals"], q["src_values"], q["src_offsets"] = adjoint_tables(
+        p, p["rec_intervals"], p["rec_values"], p["rec_offsets"], True)
+    q["rec_intervals"], q["rec_values"], q["rec_offsets"] = adjoint_tables(
+        p, p["src_intervals"], p["src_values"], p["src_offsets"], False)
+    reversed_traces = np.ascontiguousarray(p["receivers"][begin - 1:end][::-1])
+    q["wavelet"] = reversed_traces if nrec > 1 else reversed_traces.reshape(steps)
+    q["receivers"] = np.zeros((steps, nsrc), dtype=p["receivers"].dtype)
+    q["begin_timestep"], q["end_timestep"] = 1, steps
+    seconds = forward(q, kind=kind, variant=variant)
+    g = q["receivers"][::-1]
+    if p["wavelet"].ndim == 1:
+        p["wavelet"][begin - 1:end] = g.sum(axis=1) if nsrc > 1 else g[:, 0]
+    else:
+        p["wavelet"][begin - 1:end] = g
+    return seconds

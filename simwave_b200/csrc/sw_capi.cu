@@ -309,10 +309,10 @@ static double run_forward_slabs(const simwave_problem &pb, size_t begin, size_t 
     return t.total;
 }
 
-// The whole of `forward`: upload, time loop, drain.
-static double run_forward(const simwave_problem &pb, size_t begin, size_t end)
+// The whole of `forward`: upload, time loop, drain.  Throws.
+static double forward_impl(const simwave_problem &pb, size_t begin, size_t end)
 {
-    try {
+    {
         const std::vector<int> devices = slab_devices();
         if (devices.size() > 1 && pb.ndim == 3 && pb.saving_stride == 0)
             return run_forward_slabs(pb, begin, end, devices);
@@ -333,6 +333,14 @@ static double run_forward(const simwave_problem &pb, size_t begin, size_t end)
                          "+ download %.3f + teardown %.3f\n",
                          t.total, t.h2d, t.run_wall, t.loop, t.d2h, t.teardown);
         return t.total;
+    }
+}
+
+template <typename F>
+static double guarded(F &&body)
+{
+    try {
+        return body();
     } catch (const std::exception &e) {
         set_last_error(e.what());
         return -1.0;
@@ -340,6 +348,165 @@ static double run_forward(const simwave_problem &pb, size_t begin, size_t end)
         set_last_error("unknown failure");
         return -1.0;
     }
+}
+
+static double run_forward(const simwave_problem &pb, size_t begin, size_t end)
+{
+    return guarded([&] { return forward_impl(pb, begin, end); });
+}
+
+// ---------------------------------------------------------------------------
+// Adjoint operator (the reference ships only
+// `forward`, its tree is laid out for more: compiler.py:145-147,
+// middleware.py:103-104).
+//
+// F maps the source wavelets w[T][nsrc] to the receiver traces d[T][nrec] of
+// `forward` started from a zero wavefield.  This computes g = F^T d.
+//
+// One time step is U^{n+1} = P (A U^n + B U^{n-1} + S_n) with A = diag(2/D) +
+// diag(s) L, s = dt^2 v^2 / D, B = -diag(N/D), S_n = diag(s) K_src^T w[n-1], P
+// the boundary conditions, and d[n-1] = K_rec U^n.  Restricted to the
+// interior points (the halo holds zeros or Neumann mirrors), P A P equals
+// diag(s / omega) times a SYMMETRIC matrix, where omega halves the weight of a
+// point for every Neumann face it lies on (the mirrored stencil counts the
+// face plane's neighbours twice).  Hence M^T = diag(omega / s) M diag(s /
+// omega) for the whole two-level recursion, and
+//
+//     F^T d = reverse( F'( reverse(d) ) )
+//
+// where F' is the SAME forward operator with the roles of the tables
+// exchanged: the traces are injected at the receiver windows (the kernel's own
+// source scaling s, weights divided by omega) and the field is sampled at the
+// source windows (weights times omega).  omega is separable, so it folds into
+// the per-axis table weights; windows are clipped to interior points (a
+// forward window that reaches into the halo samples zeros, or mirror copies
+// under Neumann: F^T is exact for windows among the interior points, which is
+// what the dot-product tests use).  Constant density only: the variable-
+// density operator is not self-adjoint under any diagonal weight.  No new
+// kernel: the time loop, its roofline and its multi-device form are those of
+// `forward`.
+// ---------------------------------------------------------------------------
+namespace {
+template <typename T>
+struct SwappedTables {
+    std::vector<size_t> intervals, offsets;
+    std::vector<T> values;
+};
+
+template <typename T>
+SwappedTables<T> adjoint_tables(const simwave_problem &pb, const size_t *iv, const T *values,
+                                const size_t *offsets, size_t count, bool inject)
+{
+    const int ndim = pb.ndim;
+    const size_t r = pb.space_order / 2;
+    const size_t ext[3] = {pb.nz, pb.nx, pb.ny};
+    SwappedTables<T> t;
+    t.intervals.assign(iv, iv + count * 2 * ndim);
+    t.offsets.assign(1, 0);
+    for (size_t i = 0; i < count; i++) {
+        const T *w = values + offsets[i];
+        size_t kept = 0;
+        for (int ax = 0; ax < ndim; ax++) {
+            const size_t b = iv[(i * ndim + ax) * 2], e = iv[(i * ndim + ax) * 2 + 1];
+            const size_t lo = r, hi = ext[ax] - r - 1;
+            size_t cb = std::max(b, lo), ce = std::min(e, hi);
+            if (cb > ce || e < lo) {
+                cb = ce = std::min(std::max(b, lo), hi);
+                t.values.push_back(T(0));
+                kept += 1;
+            } else {
+                for (size_t k = cb; k <= ce; k++) {
+                    T v = w[k - b];
+                    const bool onBefore = pb.boundary_conditions[2 * ax] == 2 && k == lo;
+                    const bool onAfter = pb.boundary_conditions[2 * ax + 1] == 2 && k == hi;
+                    for (int f = 0; f < (int)onBefore + (int)onAfter; f++)
+                        v = inject ? v * T(2) : v * T(0.5);
+                    t.values.push_back(v);
+                }
+                kept += ce - cb + 1;
+            }
+            t.intervals[(i * ndim + ax) * 2] = cb;
+            t.intervals[(i * ndim + ax) * 2 + 1] = ce;
+            w += e - b + 1;
+        }
+        t.offsets.push_back(t.offsets.back() + kept);
+    }
+    if (t.values.empty())
+        t.values.push_back(T(0));
+    return t;
+}
+
+template <typename T>
+double adjoint_impl(const simwave_problem &pb, size_t begin, size_t end)
+{
+    if (pb.density)
+        throw Error("adjoint operator: constant density only (the variable-density "
+                    "operator is not self-adjoint)");
+    if (pb.saving_stride != 0)
+        throw Error("adjoint operator: saving_stride must be 0");
+    if (begin < 1 || end > pb.wavelet_size || begin > end)
+        throw Error("adjoint operator: timestep range outside [1, wavelet_size]");
+    const size_t nsrc = pb.num_sources, nrec = pb.num_receivers;
+    if (!nsrc || !nrec)
+        throw Error("adjoint operator needs sources and receivers");
+    const size_t steps = end - begin + 1;
+    const SwappedTables<T> inj = adjoint_tables<T>(
+        pb, pb.rec_points_interval, (const T *)pb.rec_points_values,
+        pb.rec_points_values_offset, nrec, true);
+    const SwappedTables<T> smp = adjoint_tables<T>(
+        pb, pb.src_points_interval, (const T *)pb.src_points_values,
+        pb.src_points_values_offset, nsrc, false);
+    // the traces, last row first, as one wavelet per receiver
+    const T *d = (const T *)pb.receivers;
+    std::vector<T> reversed(steps * nrec);
+    for (size_t i = 0; i < steps; i++)
+        std::memcpy(&reversed[i * nrec], d + (end - 1 - i) * nrec, nrec * sizeof(T));
+    std::vector<T> sampled(steps * nsrc, T(0));
+
+    simwave_problem q = pb;
+    q.wavelet = reversed.data();
+    q.wavelet_size = steps;
+    q.wavelet_count = nrec;
+    q.src_points_interval = inj.intervals.data();
+    q.src_points_values = inj.values.data();
+    q.src_points_values_size = inj.values.size();
+    q.src_points_values_offset = inj.offsets.data();
+    q.rec_points_interval = smp.intervals.data();
+    q.rec_points_values = smp.values.data();
+    q.rec_points_values_size = smp.values.size();
+    q.rec_points_values_offset = smp.offsets.data();
+    q.num_sources = nrec;
+    q.num_receivers = nsrc;
+    q.receivers = sampled.data();
+    const double seconds = forward_impl(q, 1, steps);
+
+    // g[begin-1+i] = sampled[steps-1-i]; one shared wavelet: the sum over sources
+    T *g = (T *)pb.wavelet;
+    const size_t wc = pb.wavelet_count > 1 ? pb.wavelet_count : 1;
+    if (wc > 1 && wc != nsrc)
+        throw Error("adjoint operator: wavelet_count must be 1 or num_sources");
+    for (size_t i = 0; i < steps; i++) {
+        const T *row = &sampled[(steps - 1 - i) * nsrc];
+        T *out = g + (begin - 1 + i) * wc;
+        if (wc > 1) {
+            std::memcpy(out, row, nsrc * sizeof(T));
+        } else {
+            T sum = T(0);
+            for (size_t k = 0; k < nsrc; k++)
+                sum += row[k];
+            out[0] = sum;
+        }
+    }
+    return seconds;
+}
+}  // namespace
+
+static double run_adjoint(const simwave_problem &pb, size_t begin, size_t end)
+{
+    return guarded([&] {
+        return pb.dtype_bytes == 4 ? adjoint_impl<float>(pb, begin, end)
+                                   : adjoint_impl<double>(pb, begin, end);
+    });
 }
 }  // namespace sw
 
@@ -544,17 +711,17 @@ void simwave_plan_destroy(simwave_plan *plan) { delete plan; }
     size_t saving_stride, T dt, size_t begin_timestep, size_t end_timestep,        \
     size_t space_order, size_t num_snapshots
 
-#define SW_DEFINE_CONSTANT(NAME, T)                                                \
-    double simwave_cuda_forward_2d_constant_##NAME(                                \
+#define SW_DEFINE_CONSTANT(OP, NAME, T)                                              \
+    double simwave_cuda_##OP##_2d_constant_##NAME(                                \
         T *u, T *velocity, T *damp, T *wavelet, size_t wavelet_size,               \
         size_t wavelet_count, T *coeff, size_t *boundary_conditions,               \
         SW_TABLE_ARGS(T), size_t nz, size_t nx, T dz, T dx, SW_TAIL_ARGS(T))       \
     {                                                                              \
         SW_FILL_COMMON(T)                                                          \
         pb.ndim = 2; pb.coeff_order2 = coeff;                                      \
-        return sw::run_forward(pb, begin_timestep, end_timestep);                  \
+        return sw::run_##OP(pb, begin_timestep, end_timestep);                  \
     }                                                                              \
-    double simwave_cuda_forward_3d_constant_##NAME(                                \
+    double simwave_cuda_##OP##_3d_constant_##NAME(                                \
         T *u, T *velocity, T *damp, T *wavelet, size_t wavelet_size,               \
         size_t wavelet_count, T *coeff, size_t *boundary_conditions,               \
         SW_TABLE_ARGS(T), size_t nz, size_t nx, size_t ny, T dz, T dx, T dy,       \
@@ -562,11 +729,11 @@ void simwave_plan_destroy(simwave_plan *plan) { delete plan; }
     {                                                                              \
         SW_FILL_COMMON(T)                                                          \
         pb.ndim = 3; pb.ny = ny; pb.dy = dy; pb.coeff_order2 = coeff;              \
-        return sw::run_forward(pb, begin_timestep, end_timestep);                  \
+        return sw::run_##OP(pb, begin_timestep, end_timestep);                  \
     }
 
-#define SW_DEFINE_VARIABLE(NAME, T)                                                \
-    double simwave_cuda_forward_2d_variable_##NAME(                                \
+#define SW_DEFINE_VARIABLE(OP, NAME, T)                                              \
+    double simwave_cuda_##OP##_2d_variable_##NAME(                                \
         T *u, T *velocity, T *density, T *damp, T *wavelet, size_t wavelet_size,   \
         size_t wavelet_count, T *coeff_order2, T *coeff_order1,                    \
         size_t *boundary_conditions, SW_TABLE_ARGS(T), size_t nz, size_t nx,       \
@@ -575,9 +742,9 @@ void simwave_plan_destroy(simwave_plan *plan) { delete plan; }
         SW_FILL_COMMON(T)                                                          \
         pb.ndim = 2; pb.density = density;                                         \
         pb.coeff_order2 = coeff_order2; pb.coeff_order1 = coeff_order1;            \
-        return sw::run_forward(pb, begin_timestep, end_timestep);                  \
+        return sw::run_##OP(pb, begin_timestep, end_timestep);                  \
     }                                                                              \
-    double simwave_cuda_forward_3d_variable_##NAME(                                \
+    double simwave_cuda_##OP##_3d_variable_##NAME(                                \
         T *u, T *velocity, T *density, T *damp, T *wavelet, size_t wavelet_size,   \
         size_t wavelet_count, T *coeff_order2, T *coeff_order1,                    \
         size_t *boundary_conditions, SW_TABLE_ARGS(T), size_t nz, size_t nx,       \
@@ -586,12 +753,18 @@ void simwave_plan_destroy(simwave_plan *plan) { delete plan; }
         SW_FILL_COMMON(T)                                                          \
         pb.ndim = 3; pb.ny = ny; pb.dy = dy; pb.density = density;                 \
         pb.coeff_order2 = coeff_order2; pb.coeff_order1 = coeff_order1;            \
-        return sw::run_forward(pb, begin_timestep, end_timestep);                  \
+        return sw::run_##OP(pb, begin_timestep, end_timestep);                  \
     }
 
-SW_DEFINE_CONSTANT(f32, float)
-SW_DEFINE_CONSTANT(f64, double)
-SW_DEFINE_VARIABLE(f32, float)
-SW_DEFINE_VARIABLE(f64, double)
+SW_DEFINE_CONSTANT(forward, f32, float)
+SW_DEFINE_CONSTANT(forward, f64, double)
+SW_DEFINE_VARIABLE(forward, f32, float)
+SW_DEFINE_VARIABLE(forward, f64, double)
+// the adjoint operator: same argument lists; `receivers` is the input,
+// `wavelet` the output (variable density is refused with an error message)
+SW_DEFINE_CONSTANT(adjoint, f32, float)
+SW_DEFINE_CONSTANT(adjoint, f64, double)
+SW_DEFINE_VARIABLE(adjoint, f32, float)
+SW_DEFINE_VARIABLE(adjoint, f64, double)
 
 }  // extern "C"

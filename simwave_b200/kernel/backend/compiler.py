@@ -20,6 +20,7 @@ import warnings
 from hashlib import sha1
 
 LANGUAGES = ('c', 'cpu_openmp', 'gpu_openmp', 'gpu_openacc', 'cuda')
+OPERATORS = ('forward', 'adjoint')
 
 _DEFAULT_CFLAGS = '-O3 -fPIC -Wall -std=c99 -shared'
 _OPENMP_FLAG = {'gcc': '-fopenmp', 'icc': '-openmp',
@@ -144,9 +145,10 @@ class Compiler:
         float_precision : str
             '-DFLOAT' or '-DDOUBLE'.
         operator : str
-            Only 'forward' exists.
+            'forward', or 'adjoint' (constant density; exported by the same
+            prebuilt library, include/simwave_cuda.h section 1b).
         """
-        if operator != 'forward':
+        if operator not in OPERATORS:
             raise ValueError("Operator {} not available.".format(operator))
 
         if self.cfile is not None:

@@ -75,14 +75,14 @@ class Middleware:
     def compiler(self):
         return self._compiler
 
-    def library(self, dimension, density, dtype):
-        """Load and return the library that exports ``forward``."""
+    def library(self, dimension, density, dtype, operator="forward"):
+        """Load and return the library that exports the operator."""
         shared_object = self.compiler.compile(
             dimension=dimension,
             density="constant_density" if density is None
             else "variable_density",
             float_precision=_PRECISION_MACRO[str(dtype)],
-            operator="forward"
+            operator=operator
         )
         return ctypes.cdll.LoadLibrary(shared_object)
 
@@ -121,23 +121,32 @@ class Middleware:
 
         if operator == 'forward':
             return self._exec_forward(**kwargs)
+        if operator == 'adjoint':
+            return self._exec_forward(_symbol='adjoint', **kwargs)
+        raise ValueError("Operator {} not available.".format(operator))
 
-    def _exec_forward(self, **kwargs):
+    def _exec_forward(self, _symbol='forward', **kwargs):
         """
         Run the forward operator; returns (u_full, shot_record), the same
         arrays that were passed in, updated in place by the kernel.
+
+        ``_symbol='adjoint'`` runs the adjoint operator through the same
+        argument list (include/simwave_cuda.h section 1b): ``shot_record`` is
+        then the input and ``wavelet`` is updated in place; returns
+        (u_full, wavelet).
         """
         velocity = kwargs['velocity_model']
         lib = self.library(
             dimension=velocity.ndim,
             density=kwargs.get('density_model'),
-            dtype=velocity.dtype
+            dtype=velocity.dtype,
+            operator=_symbol
         )
 
         types = self._argtypes(**kwargs)
         keys = [k for k in ARGUMENT_ORDER if kwargs.get(k) is not None]
 
-        forward = lib.forward
+        forward = getattr(lib, _symbol)
         forward.restype = ctypes.c_double
         forward.argtypes = [types[k] for k in keys]
 
@@ -150,11 +159,13 @@ class Middleware:
 
         if exec_time < 0:
             raise RuntimeError(
-                "forward failed: {}".format(self._last_error(lib))
+                "{} failed: {}".format(_symbol, self._last_error(lib))
             )
 
-        print('Run forward in %f seconds.' % exec_time)
+        print('Run %s in %f seconds.' % (_symbol, exec_time))
 
+        if _symbol == 'adjoint':
+            return kwargs.get('u_full'), kwargs.get('wavelet')
         return kwargs.get('u_full'), kwargs.get('shot_record')
 
     @staticmethod

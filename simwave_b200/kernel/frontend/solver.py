@@ -95,14 +95,57 @@ class Solver:
         ndarray
             Shot record.
         """
+        return self._run('forward')
+
+    def adjoint(self, shot_record):
+        """
+        Apply the adjoint of the forward operator to a shot record (new; the
+        reference stops at ``forward``).  With F the linear map from the source
+        wavelets to the shot record of ``forward()``, returns F^T applied to
+        ``shot_record``: what a gradient computation correlates with the
+        forward wavefield.  Constant density, ``saving_stride == 0``.
+
+        Parameters
+        ----------
+        shot_record : ndarray
+            Data of shape (timesteps, receivers), e.g. a residual.
+
+        Returns
+        ----------
+        ndarray
+            Last adjoint wavefield without time and space halos.
+        ndarray
+            Adjoint source of shape (timesteps, sources), or (timesteps,)
+            for a single source.
+        """
+        expected = (self.time_model.timesteps, self.receivers.count)
+        data = np.ascontiguousarray(shot_record, dtype=self.space_model.dtype)
+        if data.shape != expected:
+            raise ValueError("shot_record must have shape {}".format(expected))
+        if self.time_model.saving_stride != 0:
+            raise ValueError("adjoint needs saving_stride == 0")
+        return self._run('adjoint', data)
+
+    def _run(self, operator, shot_record=None):
         space, time = self.space_model, self.time_model
         u_full = self.u_full
+        if operator == 'adjoint':
+            count = self.sources.count
+            wavelet = np.zeros((time.timesteps, count) if count > 1
+                               else (time.timesteps,), dtype=space.dtype)
+            wavelet_count = count
+            wavelet_size = time.timesteps
+        else:
+            shot_record = self.shot_record
+            wavelet = self.wavelet.values
+            wavelet_count = self.wavelet.num_sources
+            wavelet_size = self.wavelet.timesteps
 
         # keyword names are the ones Middleware.exec unpacks into the ABI
         # argument list (middleware.py, _keys_in_order)
         arguments = {
             'u_full': u_full,
-            'shot_record': self.shot_record,
+            'shot_record': shot_record,
             'num_snapshots': u_full.shape[0],
             # model
             'velocity_model': space.extended_velocity_model,
@@ -119,9 +162,9 @@ class Solver:
             'begin_timestep': 1,
             'end_timestep': time.timesteps,
             # acquisition
-            'wavelet': self.wavelet.values,
-            'wavelet_size': self.wavelet.timesteps,
-            'wavelet_count': self.wavelet.num_sources,
+            'wavelet': wavelet,
+            'wavelet_size': wavelet_size,
+            'wavelet_count': wavelet_count,
             'num_sources': self.sources.count,
             'num_receivers': self.receivers.count,
         }
@@ -139,7 +182,7 @@ class Solver:
             'model_resident': space.model_token,
         }
 
-        u_full, recv = self._middleware.exec(operator='forward', **arguments)
+        u_full, recv = self._middleware.exec(operator=operator, **arguments)
 
         u_full = time.remove_time_halo_region(u_full)
         u_full = space.remove_halo_region(u_full)

@@ -28,8 +28,9 @@ def shim(ndim, density, dtype):
             ndim, "variable_density" if density else "constant_density",
             "-DFLOAT" if np.dtype(dtype) == np.float32 else "-DDOUBLE")
         lib = ctypes.CDLL(path)
-        lib.forward.restype = ctypes.c_double
-        lib.forward.argtypes = forward_argtypes(ndim, density, dtype)
+        for fn in (lib.forward, lib.adjoint):       # same argument list
+            fn.restype = ctypes.c_double
+            fn.argtypes = forward_argtypes(ndim, density, dtype)
         _libs[key] = lib
     return _libs[key]
 
@@ -57,6 +58,17 @@ def cuda_forward(p):
     lib = shim(p["velocity"].ndim, p.get("density") is not None,
                p["velocity"].dtype)
     seconds = lib.forward(*forward_args(p))
+    if seconds < 0:
+        raise RuntimeError(core().simwave_cuda_last_error().decode())
+    return seconds
+
+
+def cuda_adjoint(p):
+    """g = F^T d through the shim's `adjoint`: reads p['receivers'], writes
+    p['wavelet'] and p['u'] in place (include/simwave_cuda.h section 1b)."""
+    lib = shim(p["velocity"].ndim, p.get("density") is not None,
+               p["velocity"].dtype)
+    seconds = lib.adjoint(*forward_args(p))
     if seconds < 0:
         raise RuntimeError(core().simwave_cuda_last_error().decode())
     return seconds

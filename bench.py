@@ -331,12 +331,14 @@ def run_slab_leg(args, rank, world, dist, barrier, max_over_ranks, planes=None,
             return out
         slab.connect_neighbours(plan, rank, world, gather_bytes)
     times = []
-    for i in range(1 + max(1, args.steps)):
-        plan.reset()
-        barrier()
-        t = plan.run(1, T)
-        if i >= 1:
-            times.append(t)
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    with ClockSampler(local) as clocks:
+        for i in range(1 + max(1, args.steps)):
+            plan.reset()
+            barrier()
+            t = plan.run(1, T)
+            if i >= 1:
+                times.append(t)
     total = max_over_ranks(sum(times))
     plan.destroy()
     nx, ny = q["velocity"].shape[1:]
@@ -351,6 +353,7 @@ def run_slab_leg(args, rank, world, dist, barrier, max_over_ranks, planes=None,
         "value": value, "unit": "Gpts/s", "scaling": scaling,
         "ms_per_timestep": 1e3 * total / len(times) / T,
         "roofline_frac_per_gpu": value / world * bpp / peak,
+        "clocks_rank0": clocks.summary(),
         "config": {
             "workload": "slab_3d (C4-shaped): global grid %s (extended), "
                         "variable density, space_order %d, %d owned planes per "

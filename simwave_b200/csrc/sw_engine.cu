@@ -1126,10 +1126,10 @@ void Plan<T>::choose_tiling()
         int maxSmem = 0;
         SW_CUDA(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
         // default: configuration 0; large-radius variable density prefers the
-        // deeper rings of configuration 7 (then 5) where they fit (FAST layout)
+        // deeper stream ring of configuration 5 (then 7) where it fits (FAST layout)
         int cfg = 0;
         if (varden_ && r > 5) {
-            for (int c : {7, 5})
+            for (int c : {5, 7})
                 if (kTiledQuery[r](c, varden_, opt_.math, &tiledInfo_) &&
                     tiledInfo_.smemBytes <= maxSmem) {
                     cfg = c;

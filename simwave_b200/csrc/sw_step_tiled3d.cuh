@@ -70,16 +70,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
+    // try_wait suspends the warp until the phase completes or the time hint
+    // runs out; with a generous hint a waiting warp issues next to nothing
+    // (the default hint made every wait a spin of SYNCS + BRA pairs: 10 % of
+    // the issued instructions of the so-16 variable-density kernel)
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar,

@@ -190,6 +190,14 @@ class SpaceModel:
         covers the bounding box with ``grid_spacing``
         (reference model.py:210-261: RegularGridInterpolator on a meshgrid).
         """
+        if tuple(data.shape) == self.shape:
+            # The model already lives on the target grid: both sets of
+            # coordinates are the same linspace, every target point is a node
+            # of the source grid, and linear interpolation at a node returns
+            # the node's value exactly (weights 1 and 0).  Same bits as the
+            # interpolant below, without its O(ndim * N) float64 passes
+            # (minutes at 1024^3).
+            return np.array(data, dtype=self.dtype)
         bounds = self._axis_bounds()
         source_axes = tuple(
             np.linspace(lo, hi, n) for (lo, hi), n in zip(bounds, data.shape)

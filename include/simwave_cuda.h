@@ -453,7 +453,7 @@ typedef struct simwave_problem {
     const size_t *src_points_interval;      /* [num_sources][2*ndim]          */
     const void *src_points_values;
     size_t src_points_values_size;
-    const size_t *src_points_values_offset; /* [num_sources+1]                */
+    const size_t *src_points_values_offset; /* [num_sources] (only these are read) */
     const size_t *rec_points_interval;
     const void *rec_points_values;
     size_t rec_points_values_size;

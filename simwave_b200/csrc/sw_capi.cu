@@ -135,7 +135,10 @@ ClippedTables clip_tables(const size_t *iv, const void *values, const size_t *of
     const unsigned char *v = (const unsigned char *)values;
     for (size_t i = 0; i < count; i++) {
         const size_t zb = iv[i * 6], ze = iv[i * 6 + 1];
-        const size_t total = offsets[i + 1] - offsets[i];
+        // a window's weights are its per-axis vectors back to back; the caller's
+        // offset table has num_sources entries (wave.c reads offset[src] only)
+        const size_t total = (ze - zb + 1) + (iv[i * 6 + 3] - iv[i * 6 + 2] + 1) +
+                             (iv[i * 6 + 5] - iv[i * 6 + 4] + 1);
         const size_t nzw = ze - zb + 1;
         const unsigned char *wz = v + offsets[i] * elem;
         const unsigned char *rest = wz + nzw * elem;
@@ -312,6 +315,11 @@ static double run_forward_slabs(const simwave_problem &pb, size_t begin, size_t 
 // The whole of `forward`: upload, time loop, drain.  Throws.
 static double forward_impl(const simwave_problem &pb, size_t begin, size_t end)
 {
+    // the allocation caches keep this call's working set, nothing older
+    struct CacheScope {
+        CacheScope() { sw::cache_begin_call(); }
+        ~CacheScope() { sw::cache_end_call(); }
+    } cacheScope;
     {
         const std::vector<int> devices = slab_devices();
         if (devices.size() > 1 && pb.ndim == 3 && pb.saving_stride == 0)

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <future>
+#include <set>
 
 #include <type_traits>
 
@@ -82,13 +83,23 @@ Options Options::from_env()
 // allocation caches
 // ---------------------------------------------------------------------------
 namespace {
+struct CachedBlock {
+    void *p;
+    unsigned long long gen;     // forward() call during which the block came back
+};
 struct Caches {
     std::mutex mu;
-    std::multimap<std::pair<int, size_t>, void *> device;   // (ordinal, bytes) -> block
+    std::multimap<std::pair<int, size_t>, CachedBlock> device;   // (ordinal, bytes) -> block
     std::map<int, size_t> deviceBytes, deviceLimit;
-    std::multimap<size_t, void *> pinned;
+    std::multimap<size_t, CachedBlock> pinned;
     size_t pinnedBytes = 0;
+    unsigned long long gen = 0;
+    // allocations a peer process may still have mapped through CUDA IPC: freed
+    // outright, never recycled
+    std::set<void *> exported;
     bool enabled = !env_is("SIMWAVE_CUDA_CACHE", "0");
+    // SIMWAVE_CUDA_CACHE=keep: blocks stay until simwave_cuda_release_cache()
+    bool keepAll = env_is("SIMWAVE_CUDA_CACHE", "keep");
 };
 // never destroyed: no CUDA calls during static destruction
 Caches &caches()
@@ -107,7 +118,7 @@ void *device_take(size_t bytes, int *deviceOut)
         std::lock_guard<std::mutex> lk(c.mu);
         auto it = c.device.find(std::make_pair(dev, bytes));
         if (it != c.device.end()) {
-            void *p = it->second;
+            void *p = it->second.p;
             c.device.erase(it);
             c.deviceBytes[dev] -= bytes;
             return p;
@@ -129,6 +140,13 @@ void *device_take(size_t bytes, int *deviceOut)
 void device_give(void *p, size_t bytes, int dev)
 {
     Caches &c = caches();
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        if (c.exported.erase(p)) {
+            cudaFree(p);
+            return;
+        }
+    }
     if (c.enabled) {
         std::lock_guard<std::mutex> lk(c.mu);
         if (!c.deviceLimit.count(dev)) {
@@ -142,7 +160,7 @@ void device_give(void *p, size_t bytes, int dev)
         }
         const size_t limit = c.deviceLimit.count(dev) ? c.deviceLimit[dev] : 0;
         if (c.deviceBytes[dev] + bytes <= limit) {
-            c.device.emplace(std::make_pair(dev, bytes), p);
+            c.device.emplace(std::make_pair(dev, bytes), CachedBlock{p, c.gen});
             c.deviceBytes[dev] += bytes;
             return;
         }
@@ -158,7 +176,7 @@ void *pinned_take(size_t bytes)
         std::lock_guard<std::mutex> lk(c.mu);
         auto it = c.pinned.find(bytes);
         if (it != c.pinned.end()) {
-            void *p = it->second;
+            void *p = it->second.p;
             c.pinned.erase(it);
             c.pinnedBytes -= bytes;
             return p;
@@ -175,7 +193,7 @@ void pinned_give(void *p, size_t bytes)
     if (c.enabled) {
         std::lock_guard<std::mutex> lk(c.mu);
         if (c.pinnedBytes + bytes <= (512u << 20)) {
-            c.pinned.emplace(bytes, p);
+            c.pinned.emplace(bytes, CachedBlock{p, c.gen});
             c.pinnedBytes += bytes;
             return;
         }
@@ -188,14 +206,61 @@ void release_caches()
     Caches &c = caches();
     std::lock_guard<std::mutex> lk(c.mu);
     for (auto &kv : c.device)
-        cudaFree(kv.second);
+        cudaFree(kv.second.p);
     c.device.clear();
     c.deviceBytes.clear();
     for (auto &kv : c.pinned)
-        cudaFreeHost(kv.second);
+        cudaFreeHost(kv.second.p);
     c.pinned.clear();
     c.pinnedBytes = 0;
     cudaGetLastError();
+}
+
+// A drop-in forward() brackets itself with these two: what the caches hold
+// after the call is the working set of THIS call only -- blocks that came back
+// during an earlier call and were not taken again by this one are freed, so a
+// survey over changing shapes does not pile up dead blocks next to another
+// framework in the same process, while a survey over one shape still pays
+// cudaMalloc / cudaMallocHost once.
+void cache_begin_call()
+{
+    Caches &c = caches();
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.gen++;
+}
+
+void cache_end_call()
+{
+    Caches &c = caches();
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.keepAll)
+        return;
+    for (auto it = c.device.begin(); it != c.device.end();) {
+        if (it->second.gen < c.gen) {
+            cudaFree(it->second.p);
+            c.deviceBytes[it->first.first] -= it->first.second;
+            it = c.device.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    for (auto it = c.pinned.begin(); it != c.pinned.end();) {
+        if (it->second.gen < c.gen) {
+            cudaFreeHost(it->second.p);
+            c.pinnedBytes -= it->first;
+            it = c.pinned.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    cudaGetLastError();
+}
+
+void cache_mark_exported(void *base)
+{
+    Caches &c = caches();
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.exported.insert(base);
 }
 
 bool is_pinned_host(const void *p)
@@ -504,6 +569,7 @@ static void ipc_export(const void *ptr, cudaIpcMemHandle_t *handle, unsigned lon
     if (fn(&base, &size, (CUdeviceptr)ptr) != CUDA_SUCCESS)
         throw Error("cuMemGetAddressRange failed");
     SW_CUDA(cudaIpcGetMemHandle(handle, (void *)base));
+    cache_mark_exported((void *)base);
     *offset = (unsigned long long)((CUdeviceptr)ptr - base);
 }
 
@@ -873,10 +939,11 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     to_device(wavelet_, pb.wavelet, waveletSize_ * waveletCount_ * sizeof(T));
     to_device(srcIv_, pb.src_points_interval, nsrc_ * 2 * ndim_ * sizeof(size_t));
     to_device(srcVal_, pb.src_points_values, pb.src_points_values_size * sizeof(T));
-    to_device(srcOff_, pb.src_points_values_offset, (nsrc_ + 1) * sizeof(size_t));
+    // num_sources / num_receivers entries: all the reference ABI ever reads
+    to_device(srcOff_, pb.src_points_values_offset, nsrc_ * sizeof(size_t));
     to_device(recIv_, pb.rec_points_interval, nrec_ * 2 * ndim_ * sizeof(size_t));
     to_device(recVal_, pb.rec_points_values, pb.rec_points_values_size * sizeof(T));
-    to_device(recOff_, pb.rec_points_values_offset, (nrec_ + 1) * sizeof(size_t));
+    to_device(recOff_, pb.rec_points_values_offset, nrec_ * sizeof(size_t));
     recOut_.alloc(std::max<size_t>(1, waveletSize_ * nrec_) * sizeof(T));
     SW_CUDA(cudaMemsetAsync(recOut_.get(), 0, recOut_.bytes(), stream_));
     srcTab_ = {srcIv_.as<unsigned long long>(), srcVal_.as<T>(),

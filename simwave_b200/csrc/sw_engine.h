@@ -78,6 +78,10 @@ private:
 void *pinned_take(size_t bytes);
 void pinned_give(void *p, size_t bytes);
 void release_caches();
+// bracket of one drop-in forward(): afterwards the caches hold what this call
+// used and nothing older (SIMWAVE_CUDA_CACHE=keep turns the trimming off)
+void cache_begin_call();
+void cache_end_call();
 
 // true if [p, p+1) is page-locked host memory known to the CUDA driver
 bool is_pinned_host(const void *p);

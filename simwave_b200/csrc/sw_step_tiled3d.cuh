@@ -576,7 +576,33 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 fpF[h] = fpM[h] = fpS[h] = make_float2(0.0f, 0.0f);
             }
             constexpr bool SPLIT = kSplitF<float, 3, MATH>;
-            if constexpr (SPLIT) {
+#ifdef SW_EXP_NOMATH
+            // development probe (never built by default): the memory side of the
+            // kernel alone -- TMA rings, stream reads, stores -- without the
+            // neighbour loads and the stencil arithmetic (=1), or with the
+            // neighbour loads and one add per loaded pair (=2)
+            constexpr bool kRings = false;
+#if SW_EXP_NOMATH == 2
+            if (true) {
+#pragma unroll
+                for (int b = 0; b < NW; b++)
+                    acc[b & 1].sF = Pair::add(acc[b & 1].sF, we[b]);
+#pragma unroll
+                for (int ir = 1; ir <= R; ir++) {
+                    const float4 up = lds4(ctr, srow + i + ir, scol);
+                    const float4 dn = lds4(ctr, srow + i - ir, scol);
+                    acc[0].sM = Pair::add(acc[0].sM, Pair::add(make_float2(up.x, up.y), make_float2(dn.x, dn.y)));
+                    acc[1].sM = Pair::add(acc[1].sM, Pair::add(make_float2(up.z, up.w), make_float2(dn.z, dn.w)));
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+                        acc[h].sS = Pair::add(acc[h].sS, Pair::add(qv[i][h][R + ir], qv[i][h][R - ir]));
+                }
+            }
+#endif
+#else
+            constexpr bool kRings = true;
+#endif
+            if constexpr (SPLIT && kRings) {
                 // F axis in split order (sw_math.cuh, split_f_sums): every
                 // aligned window pair feeds an even-offset chain in place and an
                 // odd-offset chain with exchanged lanes; no misaligned pairs
@@ -614,7 +640,7 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
                 return (k & 1) ? make_float2(w[k], w[k + 1]) : we[k / 2];
             };
 #pragma unroll
-            for (int ir = 1; ir <= R; ir++) {
+            for (int ir = 1; ir <= (kRings ? R : 0); ir++) {
                 const float4 up = lds4(ctr, srow + i + ir, scol);
                 const float4 dn = lds4(ctr, srow + i - ir, scol);
                 const float2 upv[2] = {make_float2(up.x, up.y), make_float2(up.z, up.w)};

@@ -36,6 +36,8 @@ LIB_DIR = os.path.join(
         os.path.realpath(__file__)))),
     'lib'
 )
+# development aid: experimental builds of the same libraries (make LIB=...)
+LIB_DIR = os.environ.get('SIMWAVE_B200_LIB_DIR', LIB_DIR)
 
 
 def prebuilt_library(dimension, density, float_precision):

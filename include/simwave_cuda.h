@@ -384,6 +384,12 @@ int simwave_cuda_set_slab_devices(const int *devices, int count);
 /* Number of kernels launched by the last forward()/plan run on this thread. */
 unsigned long long simwave_cuda_last_launch_count(void);
 
+/* How the time loop of the last forward()/plan run on this thread was driven:
+ * 0 = kernels launched per time step, 1 = the persistent 2D loop with a grid
+ * barrier per step, 2 = the tile-resident 2D loop (wavefields and model kept in
+ * shared memory, halo strips exchanged between neighbouring tiles). */
+int simwave_cuda_last_loop_kind(void);
+
 /* Device buffers and pinned staging buffers are kept between calls (a survey
  * calls forward() once per shot with the same shapes); this hands every cached
  * block back to the driver.  The cache is bounded by half of the device memory

@@ -596,6 +596,8 @@ int simwave_cuda_set_hint(int hint, long long value)
 
 unsigned long long simwave_cuda_last_launch_count(void) { return sw::last_timing().launches; }
 
+int simwave_cuda_last_loop_kind(void) { return sw::last_timing().loopKind; }
+
 simwave_plan *simwave_plan_create(const simwave_problem *problem)
 {
     try {

@@ -686,6 +686,14 @@ private:
     const CUtensorMap &field_map(const T *base, bool halo);
     void choose_tiling();
     DeviceBuffer loopBarrier_;   // grid barrier word of the persistent 2D loop
+    // tile-resident 2D loop: origin of every receiver window (host copy), the
+    // tiling once chosen, receivers grouped by owner tile, per-tile step flags
+    std::vector<int> recLoM_, recLoF_;
+    int recMaxM_ = 1, recMaxF_ = 1;
+    int residentState_ = 0;      // 0 = not tried yet, 1 = available, -1 = not available
+    Loop2dTiling residentTiling_{};
+    DeviceBuffer residentRecStart_, residentRecIndex_, residentFlags_;
+    bool run_resident(LoopArgs<T> &L);
 
     cudaStream_t stream_ = nullptr;
     cudaEvent_t evBegin_ = nullptr, evEnd_ = nullptr;
@@ -965,6 +973,17 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
     };
     check_windows(pb.src_points_interval, nsrc_, "source");
     check_windows(pb.rec_points_interval, nrec_, "receiver");
+    if (ndim_ == 2) {
+        const size_t *iv = pb.rec_points_interval;
+        recLoM_.resize(nrec_);
+        recLoF_.resize(nrec_);
+        for (size_t i = 0; i < nrec_; i++) {
+            recLoM_[i] = (int)iv[i * 4];
+            recLoF_[i] = (int)iv[i * 4 + 2];
+            recMaxM_ = std::max(recMaxM_, (int)(iv[i * 4 + 1] - iv[i * 4] + 1));
+            recMaxF_ = std::max(recMaxF_, (int)(iv[i * 4 + 3] - iv[i * 4 + 2] + 1));
+        }
+    }
     {
         const size_t *iv = pb.src_points_interval;
         bool overlap = false;
@@ -1541,6 +1560,7 @@ void Plan<T>::run(size_t begin, size_t end)
 template <typename T>
 bool Plan<T>::run_persistent(size_t begin, size_t end)
 {
+    timing.loopKind = 0;
     if (ndim_ != 2 || stride_ != 0 || opt_.perStep || opt_.debug || begin > end)
         return false;
     for (size_t s = 0; s < 3; s++)
@@ -1573,11 +1593,19 @@ bool Plan<T>::run_persistent(size_t begin, size_t end)
         SW_CUDA(cudaMemsetAsync(traceBuf.get(), 0, traceBuf.bytes(), stream_));
         L.trace = traceBuf.as<unsigned long long>();
     }
-    const bool ok = varden_ ? launch_loop2d<T, true>(opt_.math, L, stream_)
-                            : launch_loop2d<T, false>(opt_.math, L, stream_);
+    // SIMWAVE_CUDA_LOOP2D=resident: the tile-resident loop
+    // (sw_loop2d_resident.cuh) where the problem fits one co-resident wave of
+    // tiles; otherwise, and by default, the grid-barrier loop
+    bool ok = run_resident(L);
+    timing.loopKind = ok ? 2 : 1;
     if (!ok)
+        ok = varden_ ? launch_loop2d<T, true>(opt_.math, L, stream_)
+                     : launch_loop2d<T, false>(opt_.math, L, stream_);
+    if (!ok) {
+        timing.loopKind = 0;
         return false;
-    check_launch("loop2d_persistent_kernel");
+    }
+    check_launch("loop2d kernel");
     if (trace) {
         unsigned long long t[256];
         SW_CUDA(cudaMemcpyAsync(t, traceBuf.get(), sizeof(t), cudaMemcpyDeviceToHost, stream_));
@@ -1593,6 +1621,71 @@ bool Plan<T>::run_persistent(size_t begin, size_t end)
         dirty_[(n + 1) % 3] = true;
     prevT_ = (end - 1) % 3; curT_ = end % 3; nextT_ = (end + 1) % 3;
     return true;
+}
+
+// The tile-resident 2D loop: needs fused boundary conditions, sources added by
+// the owning thread (or none), and a tiling that fits one wave of CTAs.
+template <typename T>
+bool Plan<T>::run_resident(LoopArgs<T> &L)
+{
+    // opt-in: measured slower than the grid-barrier loop on B200 (see the
+    // header of sw_loop2d_resident.cuh)
+    if (residentState_ < 0 || !env_is("SIMWAVE_CUDA_LOOP2D", "resident"))
+        return false;
+    if (!args_.fuse_bc || (nsrc_ > 0 && !L.fuseSources))
+        return false;
+    if (residentState_ == 0) {
+        residentState_ = -1;
+        Loop2dTiling tl{};
+        const bool fits = varden_ ? loop2d_resident_tiling<T, true>(opt_.math, g_, recMaxM_,
+                                                                    recMaxF_, &tl)
+                                  : loop2d_resident_tiling<T, false>(opt_.math, g_, recMaxM_,
+                                                                     recMaxF_, &tl);
+        if (!fits)
+            return false;
+        residentTiling_ = tl;
+        // receivers grouped by the tile that owns the first cell of their window
+        // (a window that starts in the halo belongs to the first tile of the axis)
+        const int tiles = tl.tilesM * tl.tilesF, r = g_.r;
+        std::vector<int> start(tiles + 1, 0), index(std::max<size_t>(1, nrec_));
+        auto owner = [&](size_t i) {
+            const int tmi = std::min(std::max(recLoM_[i] - r, 0) / tl.tm, tl.tilesM - 1);
+            const int tfi = std::min(std::max(recLoF_[i] - r, 0) / tl.tf, tl.tilesF - 1);
+            return tmi * tl.tilesF + tfi;
+        };
+        for (size_t i = 0; i < nrec_; i++)
+            start[owner(i) + 1]++;
+        for (int t = 0; t < tiles; t++)
+            start[t + 1] += start[t];
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (size_t i = 0; i < nrec_; i++)
+            index[fill[owner(i)]++] = (int)i;
+        residentRecStart_.alloc(start.size() * sizeof(int));
+        residentRecIndex_.alloc(index.size() * sizeof(int));
+        residentFlags_.alloc(tiles * sizeof(unsigned));
+        SW_CUDA(cudaMemcpyAsync(residentRecStart_.get(), start.data(), start.size() * sizeof(int),
+                                cudaMemcpyHostToDevice, stream_));
+        SW_CUDA(cudaMemcpyAsync(residentRecIndex_.get(), index.data(), index.size() * sizeof(int),
+                                cudaMemcpyHostToDevice, stream_));
+        SW_CUDA(cudaStreamSynchronize(stream_));     // the vectors die here
+        residentState_ = 1;
+        if (std::getenv("SIMWAVE_CUDA_VERBOSE"))
+            std::fprintf(stderr,
+                         "simwave_b200: tile-resident 2D loop, %d x %d tiles of %d x %d points, "
+                         "%zu B of shared memory per CTA\n",
+                         tl.tilesM, tl.tilesF, tl.tm, tl.tf, tl.smemBytes);
+    }
+    const Loop2dTiling &tl = residentTiling_;
+    L.tm = tl.tm; L.tf = tl.tf; L.tilesM = tl.tilesM; L.tilesF = tl.tilesF;
+    L.flags = residentFlags_.as<unsigned>();
+    L.recStart = residentRecStart_.as<int>();
+    L.recIndex = residentRecIndex_.as<int>();
+    SW_CUDA(cudaMemsetAsync(residentFlags_.get(), 0, residentFlags_.bytes(), stream_));
+    const bool ok = varden_ ? launch_loop2d_resident<T, true>(opt_.math, L, tl, stream_)
+                            : launch_loop2d_resident<T, false>(opt_.math, L, tl, stream_);
+    if (!ok)
+        residentState_ = -1;
+    return ok;
 }
 
 template <typename T>

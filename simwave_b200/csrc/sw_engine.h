@@ -34,6 +34,7 @@ struct Timing {
     double loop = 0, h2d = 0, d2h = 0, total = 0;
     double run_wall = 0, teardown = 0;   // host wall of run(); plan destruction
     unsigned long long launches = 0;
+    int loopKind = 0;   // time loop of the last run: 0 per-step launches, 1 grid-barrier 2D loop, 2 tile-resident 2D loop
 };
 
 // RAII device allocation

@@ -6,6 +6,7 @@
 #include <algorithm>
 
 #include "sw_loop2d.cuh"
+#include "sw_loop2d_resident.cuh"
 #endif
 
 namespace sw {
@@ -42,6 +43,10 @@ template void launch_step_simple<SW_T, SW_NDIM, (SW_VARDEN != 0)>(int, const Ste
 
 #if SW_NDIM == 2
 template bool launch_loop2d<SW_T, (SW_VARDEN != 0)>(int, const LoopArgs<SW_T> &, cudaStream_t);
+template bool loop2d_resident_tiling<SW_T, (SW_VARDEN != 0)>(int, const Grid &, int, int,
+                                                             Loop2dTiling *);
+template bool launch_loop2d_resident<SW_T, (SW_VARDEN != 0)>(int, const LoopArgs<SW_T> &,
+                                                             const Loop2dTiling &, cudaStream_t);
 #endif
 
 }  // namespace sw

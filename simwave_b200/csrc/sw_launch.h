@@ -26,9 +26,32 @@ struct LoopArgs {
     long long begin, end;     // time steps, inclusive
     unsigned *barrier;        // grid barrier counter, zero at launch
     unsigned long long *trace;   // phase time stamps of CTA 0 (development aid) or nullptr
+    // tile-resident loop (loop2d_resident_kernel) only: one CTA per tile of
+    // tm x tf interior points for the whole range of time steps
+    int tm, tf, tilesM, tilesF;
+    unsigned *flags;          // [tilesM * tilesF] steps completed per tile, zero at launch
+    const int *recStart;      // [tiles + 1] receivers grouped by the tile that owns the
+    const int *recIndex;      //   first cell of their window
 };
 template <typename T, bool VARDEN>
 bool launch_loop2d(int math, const LoopArgs<T> &L, cudaStream_t stream);
+
+// Tile-resident variant: every CTA keeps its tile of the wavefields and of the
+// model in shared memory across the time loop and exchanges only halo strips
+// with its neighbours (per-tile step flags instead of a grid barrier).
+struct Loop2dTiling {
+    int tm, tf, tilesM, tilesF;
+    size_t smemBytes;
+};
+// picks the tiling for grid g (false: this problem does not fit -- too many
+// tiles for one co-resident wave, or not enough shared memory); a tile is at
+// least minTm x minTf points (the largest receiver window, so that a window
+// reaches no further than a neighbouring tile)
+template <typename T, bool VARDEN>
+bool loop2d_resident_tiling(int math, const Grid &g, int minTm, int minTf, Loop2dTiling *out);
+template <typename T, bool VARDEN>
+bool launch_loop2d_resident(int math, const LoopArgs<T> &L, const Loop2dTiling &tiling,
+                            cudaStream_t stream);
 
 // ---- tiled 3D kernel (float32, constant density) ---------------------------
 struct TiledInfo {

@@ -45,6 +45,11 @@ struct Loop2dShape {
     static constexpr int ROWS =
         F32 ? (!VARDEN ? (R <= 5 ? 1 : 0) : (R <= 2 ? 1 : 0)) : (!VARDEN ? (R <= 1 ? 1 : 0) : 0);
     static constexpr int TILE_ROWS = kLoop2dGroups * (ROWS ? ROWS : 1);
+    // two-wide float32 arithmetic for the four points of a strip (FAST mode)
+    static constexpr bool PACKED = F32 && !VARDEN && ROWS == 1;
+    // threads of a CTA of the tile-resident loop (one CTA per SM): as many warps
+    // as the registers of the strip allow
+    static constexpr int RESIDENT_THREADS = PACKED ? 640 : 384;
 };
 
 // four consecutive elements through 128-bit loads / stores (16-byte aligned
@@ -130,6 +135,58 @@ struct StripNeighbours {
     __device__ __forceinline__ T M1(int k) const { return M(k); }
     __device__ __forceinline__ T S(int) const { return T(0); }
 };
+
+// The four points of a one-row strip on the two-wide float32 instructions
+// (FAST mode, constant density): every lane goes through the operations of
+// value_from_neighbours in the same order -- Stencil<float, 2, FAST>::begin /
+// ring / laplacian, then update_point -- so the result is bit-identical to the
+// scalar path at half the arithmetic instructions.
+template <int R>
+__device__ __forceinline__ void strip_values_packed(const StepArgs<float> &a,
+                                                    const Strip<float, R, 1> &t,
+                                                    const float pv[4], const float cv[4],
+                                                    const float qv[4], float out[4])
+{
+    constexpr int RP = Strip<float, R, 1>::RP;
+    // the F window of the strip: left side | my four columns | right side
+    float w[4 + 2 * RP];
+#pragma unroll
+    for (int k = 0; k < RP; k++) {
+        w[k] = t.side[0][0][k];
+        w[RP + 4 + k] = t.side[0][1][k];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        w[RP + c] = t.col[R][c];
+    const bool damped = (qv[0] != 0.0f) | (qv[1] != 0.0f) | (qv[2] != 0.0f) | (qv[3] != 0.0f);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int c = 2 * h;
+        const float2 u = make_float2(w[RP + c], w[RP + c + 1]);
+        float2 sF = Pair::mul(Pair::bc(a.c2[0]), u), sM = sF;
+#pragma unroll
+        for (int ir = 1; ir <= R; ir++) {
+            sF = ring_sum2<MATH_FAST>(sF, a.c2[ir],
+                                      make_float2(w[RP + c + ir], w[RP + c + 1 + ir]),
+                                      make_float2(w[RP + c - ir], w[RP + c + 1 - ir]));
+            sM = ring_sum2<MATH_FAST>(sM, a.c2[ir],
+                                      make_float2(t.col[R + ir][c], t.col[R + ir][c + 1]),
+                                      make_float2(t.col[R - ir][c], t.col[R - ir][c + 1]));
+        }
+        // Stencil<float, 2, FAST>::laplacian
+        float2 lo = Pair::mul(sF, Pair::bc(a.inv_h2_lo[AX_F]));
+        lo = Pair::fma(sM, Pair::bc(a.inv_h2_lo[AX_M]), lo);
+        float2 lap = Pair::fma(sF, Pair::bc(a.inv_h2[AX_F]), lo);
+        lap = Pair::fma(sM, Pair::bc(a.inv_h2[AX_M]), lap);
+        const float2 prev = make_float2(pv[c], pv[c + 1]);
+        const float2 c0 = make_float2(cv[c], cv[c + 1]);
+        const float2 q = make_float2(qv[c], qv[c + 1]);
+        const float2 o = damped ? update_pair<MATH_FAST, true>(lap, u, prev, c0, q)
+                                : update_pair<MATH_FAST, false>(lap, u, prev, c0, q);
+        out[c] = o.x;
+        out[c + 1] = o.y;
+    }
+}
 
 // Grid-wide barrier for co-resident CTAs (cooperative launch): one
 // release-increment per CTA on a monotonic counter, thread 0 spins with
@@ -300,12 +357,16 @@ loop2d_persistent_kernel(const __grid_constant__ LoopArgs<T> L)
                     load4<T>(prev + p, pv);
                     load4<T>(a.c0 + p, cv);
                     load4<T>(a.q + p, qv);
+                    if constexpr (Loop2dShape<T, R, VARDEN>::PACKED && MATH == MATH_FAST) {
+                        strip_values_packed<R>(a, su, pv, cv, qv, out[i]);
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const StripNeighbours<T, R, ROWS> nu{su, i, c};
-                        const StripNeighbours<T, R, ROWS> nd{VARDEN ? sd : su, i, c};
-                        out[i][c] = value_from_neighbours<T, 2, VARDEN, R, MATH>(a, nu, nd, pv[c],
-                                                                                cv[c], qv[c]);
+                        for (int c = 0; c < 4; c++) {
+                            const StripNeighbours<T, R, ROWS> nu{su, i, c};
+                            const StripNeighbours<T, R, ROWS> nd{VARDEN ? sd : su, i, c};
+                            out[i][c] = value_from_neighbours<T, 2, VARDEN, R, MATH>(
+                                a, nu, nd, pv[c], cv[c], qv[c]);
+                        }
                     }
                 }
                 // rows / columns clear of every face region: plain vector stores

@@ -401,6 +401,24 @@ def test_tiled_kernel_in_place_between_snapshots(monkeypatch):
 # ---------------------------------------------------------------------------
 # persistent 2D time-loop kernel against the per-step launches
 # ---------------------------------------------------------------------------
+LOOP_PER_STEP, LOOP_GRID, LOOP_RESIDENT = 0, 1, 2
+
+
+def loop_kind():
+    lib = core()
+    lib.simwave_cuda_last_loop_kind.restype = ctypes.c_int
+    return lib.simwave_cuda_last_loop_kind()
+
+
+@pytest.fixture(params=["resident", "grid"])
+def loop2d(request, monkeypatch):
+    """Both persistent 2D loops: the grid-barrier one (default) and the
+    tile-resident one (opt-in, falls back to the other where it does not fit)."""
+    if request.param == "resident":
+        monkeypatch.setenv("SIMWAVE_CUDA_LOOP2D", "resident")
+    return request.param
+
+
 @pytest.mark.parametrize("math", ["strict", "fast"])
 @pytest.mark.parametrize("shape,order,density,dtype,bc", [
     ((90, 300), 8, False, np.float32, (2, 1, 1, 1)),
@@ -409,11 +427,12 @@ def test_tiled_kernel_in_place_between_snapshots(monkeypatch):
     ((13, 14), 8, False, np.float32, (2, 2, 2, 1)),      # separate boundary passes
     ((300, 700), 2, False, np.float64, (1, 0, 0, 2))])
 def test_persistent_2d_loop_matches_per_step_launches(shape, order, density,
-                                                      dtype, bc, math,
+                                                      dtype, bc, math, loop2d,
                                                       monkeypatch):
-    """One cooperative launch for the whole time loop (sw_loop2d.cuh) must
-    reproduce the three-kernels-per-step path bit for bit: wavefield slots and
-    traces, many overlapping sources and per-source wavelets included."""
+    """One cooperative launch for the whole time loop (sw_loop2d.cuh,
+    sw_loop2d_resident.cuh) must reproduce the three-kernels-per-step path bit
+    for bit: wavefield slots and traces, many overlapping sources and
+    per-source wavelets included."""
     small = min(shape) < 20
     p = problems.make_problem(
         shape=shape, space_order=order, density=density, dtype=dtype,
@@ -426,17 +445,23 @@ def test_persistent_2d_loop_matches_per_step_launches(shape, order, density,
     per_step = problems.clone(p)
     cuda_forward(per_step)
     launches_per_step = core().simwave_cuda_last_launch_count()
+    assert loop_kind() == LOOP_PER_STEP
     monkeypatch.delenv("SIMWAVE_CUDA_LOOP")
     persistent = problems.clone(p)
     cuda_forward(persistent)
     launches_persistent = core().simwave_cuda_last_launch_count()
+    # many overlapping sources are added by a separate phase, which only the
+    # grid-barrier loop has; grids below 3r+2 take separate boundary passes
+    assert loop_kind() in (LOOP_GRID, LOOP_RESIDENT)
+    if loop2d == "grid":
+        assert loop_kind() == LOOP_GRID
     assert np.abs(per_step["u"]).max() > 0
     assert np.array_equal(per_step["u"], persistent["u"])
     assert np.array_equal(per_step["receivers"], persistent["receivers"])
     assert launches_persistent < launches_per_step / 10
 
 
-def test_persistent_2d_loop_timestep_windows():
+def test_persistent_2d_loop_timestep_windows(loop2d):
     """Two consecutive windows of the loop through the plan API equal one run."""
     from simwave_b200 import slab
     p = problems.make_problem(shape=(80, 90), space_order=6, timesteps=31, seed=2)
@@ -478,8 +503,8 @@ def test_pinned_and_pageable_host_buffers_agree():
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("density", [False, True])
 @pytest.mark.parametrize("order", [2, 4, 6, 8, 10, 12, 14, 16, 20])
-def test_persistent_2d_loop_every_radius(order, density, dtype, monkeypatch):
-    """Every strip shape of the persistent 2D kernel (rows per thread depend on
+def test_persistent_2d_loop_every_radius(order, density, dtype, loop2d, monkeypatch):
+    """Every strip shape of the persistent 2D kernels (rows per thread depend on
     radius, precision and density) against the per-step launches, bit for bit,
     on a grid whose extents are not multiples of the tile."""
     p = problems.make_problem(
@@ -493,9 +518,39 @@ def test_persistent_2d_loop_every_radius(order, density, dtype, monkeypatch):
     monkeypatch.delenv("SIMWAVE_CUDA_LOOP")
     persistent = problems.clone(p)
     cuda_forward(persistent)
+    assert loop_kind() == (LOOP_GRID if loop2d == "grid" else LOOP_RESIDENT)
     assert np.abs(per_step["u"]).max() > 0
     assert np.array_equal(per_step["u"], persistent["u"])
     assert np.array_equal(per_step["receivers"], persistent["receivers"])
+
+
+@pytest.mark.parametrize("math", ["strict", "fast"])
+@pytest.mark.parametrize("shape,order,bc,nbl", [
+    ((421, 1841), 8, (2, 1, 1, 1), ((0, 70), (70, 70))),     # Marmousi-sized: ~145 tiles
+    ((517, 517), 4, (2, 1, 0, 1), ((0, 0), (0, 0))),         # README-sized
+    ((333, 1203), 2, (2, 2, 2, 2), ((0, 9), (7, 8)))])
+def test_resident_2d_loop_many_tiles(shape, order, bc, nbl, math, monkeypatch):
+    """The tile-resident loop on grids that fill the whole device with tiles:
+    halo strips from every neighbour, receivers along a line that crosses many
+    tiles (windows straddling tile corners), a source next to a tile corner,
+    Neumann / Dirichlet faces on the edge tiles -- bit for bit against the
+    per-step launches."""
+    p = problems.make_problem(
+        shape=shape, space_order=order, timesteps=60, bc=bc, seed=order + 3,
+        nbl=nbl, num_sources=2, src_radius=4, num_receivers=300, rec_radius=4)
+    monkeypatch.setenv("SIMWAVE_CUDA_MATH", math)
+    monkeypatch.setenv("SIMWAVE_CUDA_LOOP", "launch")
+    per_step = problems.clone(p)
+    cuda_forward(per_step)
+    monkeypatch.delenv("SIMWAVE_CUDA_LOOP")
+    monkeypatch.setenv("SIMWAVE_CUDA_LOOP2D", "resident")
+    resident = problems.clone(p)
+    cuda_forward(resident)
+    assert loop_kind() == LOOP_RESIDENT
+    assert np.abs(per_step["u"]).max() > 0
+    assert np.abs(per_step["receivers"]).max() > 0
+    assert np.array_equal(per_step["u"], resident["u"])
+    assert np.array_equal(per_step["receivers"], resident["receivers"])
 
 
 # ---------------------------------------------------------------------------

@@ -38,9 +38,12 @@ def without_receivers(p):
 
 def main():
     p = workloads.marmousi_2d(timesteps=600)
-    for mode in ("persistent", "launch"):
+    c1 = workloads.readme_2d(timesteps=300)
+    for mode in ("resident", "grid", "launch"):
+        os.environ["SIMWAVE_CUDA_LOOP2D"] = mode
         if mode == "launch":
             os.environ["SIMWAVE_CUDA_LOOP"] = "launch"
+        timed(c1, "readme 2D, 512 receivers [%s]" % mode)
         timed(p, "marmousi, 1700 receivers [%s]" % mode)
         timed(without_receivers(p), "marmousi, 1 receiver [%s]" % mode)
         q = without_receivers(p)

@@ -29,6 +29,8 @@ Printed JSON line (rank 0):
             grid itself split N ways (strong, N > 1)
   survey    C5: 64 shots x 512^3 through forward(), shot s on rank s mod N
   configs_2d  (N = 1) C1 and C2: device loop, forward() and the CPU kernel
+  c3_f64    (N = 1) C3 in float64, the precision the reference's own benchmark
+            script uses: device loop over 300 time steps, 40 B per point
 
 `--impl reference` times the reference's own CPU implementation alone.
 Under torchrun every rank simulates its own shot of the workload (shot
@@ -50,9 +52,17 @@ for _p in (REPO, os.path.join(REPO, "tests")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-# thread placement for the CPU baseline must be set before libgomp loads
-os.environ.setdefault("OMP_PROC_BIND", "true")
-os.environ.setdefault("OMP_PLACES", "cores")
+# Thread placement of the CPU arm must be in the environment before libgomp
+# loads -- but ONLY in a process that runs nothing else: with OMP_PROC_BIND set,
+# libgomp pins the main thread to one core when it initialises (at `import
+# torch`), every thread created later inherits that one-core mask, and the
+# staging / drain / prefault threads of the CUDA library then share a single
+# core (measured: pageable uploads 5 GB/s instead of 27; under torchrun all
+# ranks' main threads land on core 0).  The GPU arm therefore runs its
+# cpu_baseline legs in a child process (cpu_reference_child).
+if "--impl" in sys.argv and "reference" in sys.argv or "--cpu-child" in sys.argv:
+    os.environ.setdefault("OMP_PROC_BIND", "true")
+    os.environ.setdefault("OMP_PLACES", "cores")
 
 import numpy as np  # noqa: E402
 
@@ -91,6 +101,12 @@ def parse():
     ap.add_argument("--no-survey", action="store_true")
     ap.add_argument("--no-2d", action="store_true",
                     help="skip the two 2D configurations (C1, C2; N = 1 only)")
+    ap.add_argument("--cpu-child", action="store_true",
+                    help="internal: time the reference's CPU kernel on "
+                         "--cpu-timesteps steps of --workload and print one JSON line")
+    ap.add_argument("--no-f64", action="store_true",
+                    help="skip the float64 C3 leg (N = 1 only)")
+    ap.add_argument("--f64-timesteps", type=int, default=300)
     ap.add_argument("--no-api", action="store_true",
                     help="skip the e2e_api leg (Solver.forward, N = 1 only)")
     return ap.parse_args()
@@ -214,6 +230,38 @@ def cpu_reference_run(p, timesteps, variant="ompfast"):
     q["end_timestep"] = timesteps
     seconds = oracle.forward(q, kind=kind, variant=variant)
     return seconds, kind, variant
+
+
+def cpu_reference_child(workload, timesteps, builder_timesteps=None):
+    """The reference's cpu_openmp kernel on the first `timesteps` steps of a
+    named workload, in a child process of its own (all host threads, bound to
+    cores), after one warm-up run.  Returns (seconds, kind, variant)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-child", "--workload", workload,
+           "--cpu-timesteps", str(int(timesteps))]
+    if builder_timesteps:
+        cmd += ["--timesteps", str(int(builder_timesteps))]
+    env = dict(os.environ)
+    env.update({"OMP_NUM_THREADS": str(host_threads()), "OMP_PROC_BIND": "true",
+                "OMP_PLACES": "cores", "CUDA_VISIBLE_DEVICES": ""})
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1200)
+    for line in reversed(out.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            r = json.loads(line)
+            return r["seconds"], r["kind"], r["variant"]
+    raise RuntimeError("CPU child failed: " + (out.stderr.strip().splitlines() or ["?"])[-1])
+
+
+def run_cpu_child(args):
+    import workloads
+    kwargs = {"timesteps": args.timesteps} if args.timesteps else {}
+    p = workloads.WORKLOADS[args.workload](**kwargs)
+    n = set_cpu_threads()
+    steps = args.cpu_timesteps or p["end_timestep"]
+    cpu_reference_run(p, min(steps, 2))          # warm the pages / threads
+    seconds, kind, variant = cpu_reference_run(p, steps)
+    print(json.dumps({"seconds": seconds, "kind": kind, "variant": variant, "threads": n}))
 
 
 def _host_threads():
@@ -496,9 +544,7 @@ def run_2d_config(name, args, barrier):
     }
     if not args.no_cpu:
         try:
-            set_cpu_threads()
-            cpu_reference_run(p, min(T, 20))
-            sec, kind, variant = cpu_reference_run(p, T)
+            sec, kind, variant = cpu_reference_child(name, T)
             out["cpu_baseline"] = {
                 "value": pts * T / sec / 1e9, "unit": "Gpts/s", "cores": host_threads(),
                 "kind": "reference" if kind == "ref" else "port",
@@ -506,6 +552,40 @@ def run_2d_config(name, args, barrier):
         except Exception as e:
             out["cpu_baseline"] = {"value": None, "sample": "failed: %s" % e}
     return out
+
+
+def run_f64_config(args):
+    """C3 in float64 -- the precision simwave's own benchmark script builds its
+    model in (benchmark/overthrust_3D.py:82) -- on one GPU: device-resident
+    loop (plan API, CUDA events) over a bounded number of time steps, against
+    the 40 B per grid-point update of the float64 fields."""
+    import workloads
+    from simwave_b200 import slab
+    T = args.f64_timesteps
+    p = workloads.overthrust_3d(timesteps=T, dtype=np.float64)
+    pts = workloads.interior_points(p)
+    bpp = workloads.bytes_per_point(p)
+    plan = slab.Plan(p)
+    times = []
+    for i in range(3):
+        plan.reset()
+        t = plan.run(1, T)
+        if i >= 1:
+            times.append(t)
+    launches = plan.launches()
+    plan.destroy()
+    from cuda_abi import core
+    core().simwave_cuda_release_cache()
+    dev = sum(times) / len(times)
+    peak, _ = measured_peak()
+    return {
+        "value": pts * T / dev / 1e9, "unit": "Gpts/s", "dtype": "f64",
+        "ms_per_timestep": 1e3 * dev / T, "timesteps": T,
+        "bytes_per_point": bpp,
+        "roofline_frac": pts * T / dev * bpp / 1e9 / peak,
+        "gpu_launches": int(launches),
+        "config": workload_config(args, p, T),
+    }
 
 
 def run_ours(args, p, rank, world, local_rank):
@@ -693,14 +773,12 @@ def run_ours(args, p, rank, world, local_rank):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sample = args.cpu_timesteps or max(1, int(3e9 // pts))
-        set_cpu_threads()
         try:
-            cpu_reference_run(p, 1)      # warm the pages / threads
-            s, kind, variant = cpu_reference_run(p, sample)
+            s, kind, variant = cpu_reference_child(args.workload, sample, args.timesteps)
             cpu = {"value": pts * sample / s / 1e9, "unit": "Gpts/s",
                    "cores": host_threads(),
                    "kind": "reference" if kind == "ref" else "port",
-                   "sample": "%d of %d time steps of the same arrays, "
+                   "sample": "%d of %d time steps of the same workload (child process), "
                              "%s build, OMP_PROC_BIND=true" % (
                                  sample, p["full_timesteps"], variant)}
         except Exception as e:   # the baseline must not sink the bench line
@@ -742,6 +820,14 @@ def run_ours(args, p, rank, world, local_rank):
             except Exception as e:
                 configs_2d[name] = {"error": "%s: %s" % (type(e).__name__, e)}
 
+    # ---- C3 in float64, as the reference's benchmark script runs it (N == 1) ---
+    c3_f64 = None
+    if world == 1 and not args.no_f64 and p is not None and p.get("name") == "overthrust_3d":
+        try:
+            c3_f64 = run_f64_config(args)
+        except Exception as e:
+            c3_f64 = {"error": "%s: %s" % (type(e).__name__, e)}
+
     if rank == 0:
         line = {
             "metric": "Gpts/s", "value": value, "unit": "Gpts/s",
@@ -769,6 +855,7 @@ def run_ours(args, p, rank, world, local_rank):
             "slab_strong": slab_strong,
             "survey": survey,
             "configs_2d": configs_2d,
+            "c3_f64": c3_f64,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "wall_ms_per_step": 1e3 * wall / args.steps,
@@ -786,6 +873,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     import workloads
     builder = workloads.WORKLOADS[args.workload]
+    if args.cpu_child:
+        run_cpu_child(args)
+        return
     if args.impl == "reference" and rank != 0:
         return
     kwargs = {}

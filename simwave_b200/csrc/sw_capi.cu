@@ -266,7 +266,10 @@ static double run_forward_slabs(const simwave_problem &pb, size_t begin, size_t 
     };
     std::vector<std::thread> threads;
     for (int k = 0; k < world; k++)
-        threads.emplace_back(slab_thread, k);
+        threads.emplace_back([&slab_thread, k] {
+            sw::widen_helper_affinity();     // one launch thread per device, not one core for all
+            slab_thread(k);
+        });
     for (auto &t : threads)
         t.join();
     if (meet.failed())
@@ -326,6 +329,7 @@ static double forward_impl(const simwave_problem &pb, size_t begin, size_t end)
             return run_forward_slabs(pb, begin, end, devices);
         const double t0 = wall();
         std::unique_ptr<PlanBase> plan = make_plan(pb, current_options());
+        plan->prefault_outputs(end);      // host pages of `u`, behind the time loop
         if (begin <= end)
             plan->run(begin, end);
         plan->download(nullptr, nullptr);

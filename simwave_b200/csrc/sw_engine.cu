@@ -10,7 +10,11 @@
 // the same history as in the reference.
 #include "sw_engine.h"
 
+#include <sched.h>
+#include <sys/mman.h>
+
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -19,6 +23,8 @@
 #include <set>
 
 #include <type_traits>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "sw_launch.h"
 #include "sw_points.cuh"
@@ -32,6 +38,15 @@ static double wall()
 }
 
 // phase log of the upload (printed under SIMWAVE_CUDA_VERBOSE)
+// NVTX range for the lifetime of the object: the phases of a call show up in
+// Nsight Systems / ncu timelines (costs nothing without a tool attached)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+
 struct PhaseLog {
     bool on;
     double t;
@@ -39,6 +54,7 @@ struct PhaseLog {
     PhaseLog() : on(std::getenv("SIMWAVE_CUDA_VERBOSE") != nullptr), t(wall()) {}
     void mark(const char *what)
     {
+        nvtxMarkA(what);
         if (!on) return;
         const double now = wall();
         char buf[96];
@@ -273,25 +289,128 @@ bool is_pinned_host(const void *p)
     return attr.type == cudaMemoryTypeHost;
 }
 
+// Helper threads inherit the CPU mask of the thread that creates them.  An
+// OpenMP runtime started with OMP_PROC_BIND pins the application's main thread
+// to ONE core when it initialises (libgomp does so at `import torch`), and
+// helpers that are meant to run side by side would then share that core
+// (measured: staged uploads at 5 GB/s instead of 27).  A helper that finds
+// itself with a one-CPU mask on a larger machine therefore asks for every CPU
+// the process may use (the kernel intersects the request with the cgroup's
+// cpuset).  SIMWAVE_CUDA_HELPER_AFFINITY=inherit keeps the inherited mask,
+// =all widens unconditionally.
+void widen_helper_affinity()
+{
+    const char *mode = std::getenv("SIMWAVE_CUDA_HELPER_AFFINITY");
+    if (mode && std::strcmp(mode, "inherit") == 0)
+        return;
+    cpu_set_t cur;
+    CPU_ZERO(&cur);
+    if (sched_getaffinity(0, sizeof(cur), &cur) != 0)
+        return;
+    const bool all = mode && std::strcmp(mode, "all") == 0;
+    if (!all && !(CPU_COUNT(&cur) == 1 && std::thread::hardware_concurrency() > 1))
+        return;
+    cpu_set_t want;
+    CPU_ZERO(&want);
+    for (int i = 0; i < CPU_SETSIZE; i++)
+        CPU_SET(i, &want);
+    sched_setaffinity(0, sizeof(want), &want);   // best effort
+}
+
+// Host-side copies between pageable arrays and the pinned staging buffers.
+// One core of these hosts moves ~2-3 GB/s, the PCIe link 50: the copy is cut
+// into pieces for a pool of helper threads that lives as long as the process
+// (SIMWAVE_CUDA_COPY_THREADS, default half of the cores, 4..16); callers --
+// the upload of a plan, its drain thread, the per-device threads of a slab
+// run -- share the pool and take part in their own copy.
+namespace {
+class CopyPool {
+public:
+    struct Piece {
+        char *dst;
+        const char *src;
+        size_t bytes;
+        std::atomic<int> *left;
+    };
+    static CopyPool &get()
+    {
+        static CopyPool *p = new CopyPool;    // never destroyed: no joins at exit
+        return *p;
+    }
+    void run(char *dst, const char *src, size_t bytes)
+    {
+        const size_t kMinPiece = 1u << 20;
+        const size_t parts = std::min<size_t>(threads_.size() + 1, std::max<size_t>(1, bytes / kMinPiece));
+        if (parts <= 1) {
+            std::memcpy(dst, src, bytes);
+            return;
+        }
+        const size_t part = (bytes / parts + 4095) & ~size_t(4095);
+        std::atomic<int> left{0};
+        size_t mine = std::min(part, bytes);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (size_t b = mine; b < bytes; b += part) {
+                left.fetch_add(1, std::memory_order_relaxed);
+                queue_.push_back(Piece{dst + b, src + b, std::min(part, bytes - b), &left});
+            }
+        }
+        cv_.notify_all();
+        std::memcpy(dst, src, mine);
+        // help with whatever is queued (mine or another caller's), then wait
+        for (;;) {
+            Piece pc;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (queue_.empty())
+                    break;
+                pc = queue_.front();
+                queue_.pop_front();
+            }
+            std::memcpy(pc.dst, pc.src, pc.bytes);
+            pc.left->fetch_sub(1, std::memory_order_release);
+        }
+        while (left.load(std::memory_order_acquire) != 0)
+            std::this_thread::yield();
+    }
+
+private:
+    CopyPool()
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        int n = (int)std::min(16u, std::max(4u, (hw ? hw : 8u) / 2));
+        if (const char *e = std::getenv("SIMWAVE_CUDA_COPY_THREADS"))
+            n = std::max(1, std::min(64, std::atoi(e)));
+        for (int i = 0; i < n - 1; i++)
+            threads_.emplace_back([this] { worker(); });
+        for (auto &t : threads_)
+            t.detach();
+    }
+    void worker()
+    {
+        widen_helper_affinity();
+        for (;;) {
+            Piece pc;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return !queue_.empty(); });
+                pc = queue_.front();
+                queue_.pop_front();
+            }
+            std::memcpy(pc.dst, pc.src, pc.bytes);
+            pc.left->fetch_sub(1, std::memory_order_release);
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Piece> queue_;
+    std::vector<std::thread> threads_;
+};
+}  // namespace
+
 void parallel_memcpy(void *dst, const void *src, size_t bytes)
 {
-    const size_t kMinPerThread = 4u << 20;
-    unsigned hw = std::thread::hardware_concurrency();
-    size_t n = std::min<size_t>(std::min<size_t>(hw ? hw : 1, 4), bytes / kMinPerThread);
-    if (n <= 1) {
-        std::memcpy(dst, src, bytes);
-        return;
-    }
-    std::vector<std::thread> th;
-    const size_t part = (bytes / n + 63) & ~size_t(63);
-    for (size_t t = 1; t < n; t++) {
-        const size_t b = t * part, e = std::min(bytes, b + part);
-        if (b < e)
-            th.emplace_back([=] { std::memcpy((char *)dst + b, (const char *)src + b, e - b); });
-    }
-    std::memcpy(dst, src, std::min(part, bytes));
-    for (auto &x : th)
-        x.join();
+    CopyPool::get().run((char *)dst, (const char *)src, bytes);
 }
 
 void DeviceBuffer::alloc(size_t bytes)
@@ -365,6 +484,7 @@ void HostDrain::ensure_staging()
 
 void HostDrain::worker()
 {
+    widen_helper_affinity();
     cudaSetDevice(device_);
     for (;;) {
         Job job;
@@ -402,15 +522,25 @@ void HostDrain::worker()
             };
             if (chunks)
                 issue(0);
+            double tWait = 0, tCopy = 0;
             for (size_t c = 0; c < chunks; c++) {
+                const double a0 = wall();
                 SW_CUDA(cudaEventSynchronize(copied_[c & 1]));
                 if (c + 1 < chunks)
                     issue(c + 1);  // overlaps with the memcpy below
+                const double a1 = wall();
                 const size_t r0 = c * rowsPerChunk;
                 const size_t nr = std::min(rowsPerChunk, job.rows - r0);
                 parallel_memcpy((char *)job.dst + r0 * job.rowBytes, pinned_[c & 1],
                                 nr * job.rowBytes);
+                tWait += a1 - a0;
+                tCopy += wall() - a1;
             }
+            if (chunks && std::getenv("SIMWAVE_CUDA_VERBOSE"))
+                std::fprintf(stderr,
+                             "simwave_b200: drain of %.0f MB through staging: %.1f ms waiting for "
+                             "the DMA, %.1f ms copying to the caller's pages\n",
+                             job.rows * job.rowBytes / 1e6, 1e3 * tWait, 1e3 * tCopy);
         } catch (const std::exception &e) {
             std::lock_guard<std::mutex> lk(mu_);
             if (error_.empty())
@@ -441,6 +571,8 @@ static bool all_zero(const void *p, size_t bytes)
     const int nthreads = (bytes > (64u << 20)) ? (int)std::min(16u, std::max(3u, hw) - 1) : 1;
     std::vector<char> nz(nthreads, 0);
     auto scan = [&](int t) {
+        if (nthreads > 1)
+            widen_helper_affinity();
         const size_t b = words * t / nthreads, e = words * (t + 1) / nthreads;
         const size_t blk = 4096;
         for (size_t i = b; i < e; i += blk) {
@@ -505,6 +637,18 @@ static const TiledLaunchFn kTiledLaunch[kMaxRadius + 1] = {
     nullptr, tiled3d_launch_r1, tiled3d_launch_r2, tiled3d_launch_r3, tiled3d_launch_r4,
     tiled3d_launch_r5, tiled3d_launch_r6, tiled3d_launch_r7, tiled3d_launch_r8,
     tiled3d_launch_r9, tiled3d_launch_r10};
+
+typedef bool (*Tiled64QueryFn)(TiledInfo *);
+typedef bool (*Tiled64LaunchFn)(int, const StepArgs<double> &, const StepMaps &,
+                                const unsigned char *, int, cudaStream_t);
+static const Tiled64QueryFn kTiled64Query[kMaxRadius + 1] = {
+    nullptr, tiled3d64_query_r1, tiled3d64_query_r2, tiled3d64_query_r3, tiled3d64_query_r4,
+    tiled3d64_query_r5, tiled3d64_query_r6, tiled3d64_query_r7, tiled3d64_query_r8,
+    tiled3d64_query_r9, tiled3d64_query_r10};
+static const Tiled64LaunchFn kTiled64Launch[kMaxRadius + 1] = {
+    nullptr, tiled3d64_launch_r1, tiled3d64_launch_r2, tiled3d64_launch_r3, tiled3d64_launch_r4,
+    tiled3d64_launch_r5, tiled3d64_launch_r6, tiled3d64_launch_r7, tiled3d64_launch_r8,
+    tiled3d64_launch_r9, tiled3d64_launch_r10};
 
 // ---------------------------------------------------------------------------
 // slab decomposition plumbing
@@ -623,6 +767,7 @@ public:
     ~Plan() override;
     void run(size_t begin, size_t end) override;
     void download(void *u, void *receivers) override;
+    void prefault_outputs(size_t end) override;
     void reset() override;
     void slab_export(void *desc) override;
     void slab_connect(const void *up, const void *down) override;
@@ -634,6 +779,8 @@ private:
 
     void check_launch(const char *what);
     T *field_base(const DeviceBuffer &b) const { return b.as<T>() + guard_ + g_.lpad; }
+    // F halo of a TMA box in elements: the radius rounded up to 16 bytes
+    static int halo_f(int r) { return sizeof(T) == 4 ? (r + 3) / 4 * 4 : (r + 1) / 2 * 2; }
     void new_field(DeviceBuffer &b);
     T *acquire();
     void give_back(T *buf);
@@ -694,6 +841,14 @@ private:
     Loop2dTiling residentTiling_{};
     DeviceBuffer residentRecStart_, residentRecIndex_, residentFlags_;
     bool run_resident(LoopArgs<T> &L);
+    std::thread prefault_;       // see PlanBase::prefault_outputs
+    std::atomic<bool> prefaultStop_{false};
+    void join_prefault()
+    {
+        if (prefault_.joinable()) {
+            prefault_.join();
+        }
+    }
 
     cudaStream_t stream_ = nullptr;
     cudaEvent_t evBegin_ = nullptr, evEnd_ = nullptr;
@@ -748,6 +903,7 @@ template <typename T>
 Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
 {
     const double t0 = wall();
+    NvtxRange nvtx("simwave_b200: upload");
     PhaseLog phases;
     ndim_ = pb.ndim;
     varden_ = pb.density != nullptr;
@@ -1053,6 +1209,8 @@ Plan<T>::Plan(const simwave_problem &pb, const Options &opt) : opt_(opt)
 template <typename T>
 Plan<T>::~Plan()
 {
+    prefaultStop_.store(true);
+    join_prefault();
     drain_.reset();   // joins the worker before buffers go away
     if (recStream_) {
         cudaStreamSynchronize(recStream_);
@@ -1204,8 +1362,11 @@ template <typename T>
 void Plan<T>::choose_tiling()
 {
     useTiled_ = false;
-    if constexpr (std::is_same<T, float>::value) {
-        if (opt_.simple || ndim_ != 3 || (varden_ && args_.quirk))
+    constexpr bool kF32 = std::is_same<T, float>::value;
+    {
+        // float32: every 3D variant but the stride-quirk case; float64:
+        // constant density (sw_step_tiled3d64.cuh)
+        if (opt_.simple || ndim_ != 3 || (varden_ && (args_.quirk || !kF32)))
             return;
         const int r = g_.r;
         // default configuration, overridable as SIMWAVE_CUDA_TILE=<cfg>[:<zchunk>]
@@ -1214,7 +1375,7 @@ void Plan<T>::choose_tiling()
         // default: configuration 0; large-radius variable density prefers the
         // deeper stream ring of configuration 5 (then 7) where it fits (FAST layout)
         int cfg = 0;
-        if (varden_ && r > 5) {
+        if (kF32 && varden_ && r > 5) {
             for (int c : {5, 7})
                 if (kTiledQuery[r](c, varden_, opt_.math, &tiledInfo_) &&
                     tiledInfo_.smemBytes <= maxSmem) {
@@ -1228,8 +1389,13 @@ void Plan<T>::choose_tiling()
             if (const char *c = std::strchr(e, ':'))
                 zchunk = std::atoi(c + 1);
         }
-        if (!kTiledQuery[r](cfg, varden_, opt_.math, &tiledInfo_))
-            throw Error("SIMWAVE_CUDA_TILE: no such tile configuration");
+        if (kF32) {
+            if (!kTiledQuery[r](cfg, varden_, opt_.math, &tiledInfo_))
+                throw Error("SIMWAVE_CUDA_TILE: no such tile configuration");
+        } else {
+            cfg = 0;
+            kTiled64Query[r](&tiledInfo_);
+        }
         if (tiledInfo_.smemBytes > maxSmem)
             return;   // plain kernel
         tiledCfg_ = cfg;
@@ -1250,8 +1416,8 @@ void Plan<T>::choose_tiling()
                                                 2048 / threads));
             resident = std::min(resident, tiledInfo_.minBlocks);
             const double slots = (double)sms * resident;
-            const double haloBytes = 4.0 * (tiledInfo_.tileM() + 2 * r) *
-                                     (tiledInfo_.tileF() + 2 * ((r + 3) / 4 * 4)) /
+            const double haloBytes = (double)sizeof(T) * (tiledInfo_.tileM() + 2 * r) *
+                                     (tiledInfo_.tileF() + 2 * halo_f(r)) /
                                      ((double)tiledInfo_.tileM() * tiledInfo_.tileF());
             double best = -1;
             int bestChunks = 1;
@@ -1260,7 +1426,7 @@ void Plan<T>::choose_tiling()
                 const int real = (interior + len - 1) / len;
                 const double waves = tilesF * tilesM * real / slots;
                 const double fill = waves / std::ceil(waves);
-                const double alg = varden_ ? 36.0 : 20.0;
+                const double alg = (varden_ ? 36.0 : 20.0) * sizeof(T) / 4;
                 const double traffic = alg / (alg + 2.0 * r * haloBytes / len);
                 const double score = fill * traffic;
                 if (score > best + 1e-9) { best = score; bestChunks = chunks; }
@@ -1271,7 +1437,7 @@ void Plan<T>::choose_tiling()
         useTiled_ = true;
         // few sources whose windows lie among the interior points: the step
         // kernel adds them itself (SIMWAVE_CUDA_SOURCES=kernel keeps the launch)
-        srcFusedTiled_ = srcInterior_ && nsrc_ <= 8 && srcMode_ != SRC_ATOMIC &&
+        srcFusedTiled_ = kF32 && srcInterior_ && nsrc_ <= 8 && srcMode_ != SRC_ATOMIC &&
                          !env_is("SIMWAVE_CUDA_SOURCES", "kernel");
 
         // per (plane, tile) flag: does the damping profile act inside the tile?
@@ -1279,9 +1445,9 @@ void Plan<T>::choose_tiling()
             model_->qflags.alloc((size_t)g_.nS * tilesM * tilesF);
             SW_CUDA(cudaMemsetAsync(model_->qflags.get(), 0, model_->qflags.bytes(), stream_));
             dim3 grid((unsigned)tilesF, (unsigned)tilesM, (unsigned)interior);
-            qflag_kernel<<<grid, 128, 0, stream_>>>(g_, field_base(model_->q), tiledInfo_.tileM(),
-                                                    tiledInfo_.tileF(),
-                                                    model_->qflags.as<unsigned char>());
+            qflag_kernel<T><<<grid, 128, 0, stream_>>>(g_, field_base(model_->q),
+                                                       tiledInfo_.tileM(), tiledInfo_.tileF(),
+                                                       model_->qflags.as<unsigned char>());
             check_launch("qflag_kernel");
             if (varden_ && !model_->frF.get()) {
                 new_field(model_->frF);
@@ -1289,11 +1455,11 @@ void Plan<T>::choose_tiling()
                 new_field(model_->frS);
                 dim3 gg((g_.nF - 2 * r + 127) / 128, g_.nM - 2 * r, interior);
                 if (opt_.math == MATH_STRICT)
-                    rho_gradient_kernel<float, MATH_STRICT><<<gg, 128, 0, stream_>>>(
+                    rho_gradient_kernel<T, MATH_STRICT><<<gg, 128, 0, stream_>>>(
                         args_, field_base(model_->frF), field_base(model_->frM),
                         field_base(model_->frS));
                 else
-                    rho_gradient_kernel<float, MATH_FAST><<<gg, 128, 0, stream_>>>(
+                    rho_gradient_kernel<T, MATH_FAST><<<gg, 128, 0, stream_>>>(
                         args_, field_base(model_->frF), field_base(model_->frM),
                         field_base(model_->frS));
                 check_launch("rho_gradient_kernel");
@@ -1325,11 +1491,13 @@ const CUtensorMap &Plan<T>::field_map(const T *base, bool halo)
     const cuuint64_t dims[3] = {(cuuint64_t)g_.pitch, (cuuint64_t)g_.nM, (cuuint64_t)g_.nS};
     const cuuint64_t strides[2] = {(cuuint64_t)g_.pitch * sizeof(T),
                                    (cuuint64_t)g_.planeStride * sizeof(T)};
-    const int rp = (g_.r + 3) / 4 * 4;
+    const int rp = halo_f(g_.r);
     const cuuint32_t box[3] = {(cuuint32_t)(tiledInfo_.tileF() + (halo ? 2 * rp : 0)),
                                (cuuint32_t)(tiledInfo_.tileM() + (halo ? 2 * g_.r : 0)), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult rc = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, rowStart, dims, strides,
+    const CUtensorMapDataType dtype = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                     : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    CUresult rc = encode_tiled_fn()(&m, dtype, 3, rowStart, dims, strides,
                                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1342,6 +1510,22 @@ const CUtensorMap &Plan<T>::field_map(const T *base, bool halo)
 template <typename T>
 void Plan<T>::launch_step(const StepArgs<T> &a)
 {
+    if constexpr (std::is_same<T, double>::value) {
+        if (useTiled_) {
+            StepMaps maps;
+            std::memset(&maps, 0, sizeof(maps));
+            maps.prefetch = opt_.prefetch >= 0 ? opt_.prefetch : 2;
+            maps.cur = field_map(a.cur, true);
+            maps.prev = field_map(a.prev, false);
+            maps.c0 = field_map(a.c0, false);
+            maps.q = field_map(a.q, false);
+            if (!kTiled64Launch[g_.r](opt_.math, a, maps, model_->qflags.as<unsigned char>(),
+                                      zChunk_, stream_))
+                throw Error("tiled float64 kernel vanished");
+            check_launch("tiled float64 step kernel");
+            return;
+        }
+    }
     if constexpr (std::is_same<T, float>::value) {
         if (useTiled_) {
             StepMaps maps;
@@ -1463,6 +1647,7 @@ void Plan<T>::run(size_t begin, size_t end)
         throw Error("timestep range outside [1, wavelet_size]");
     if ((slabUp_ || slabDown_) && !slabConnected_)
         throw Error("slab plan is not connected to its neighbours");
+    NvtxRange nvtx("simwave_b200: time loop");
     const double t0 = wall();
     SW_CUDA(cudaEventRecord(evBegin_, stream_));
     if (recBegin_ == recEnd_) { recBegin_ = begin - 1; recEnd_ = begin - 1; }
@@ -1688,9 +1873,57 @@ bool Plan<T>::run_resident(LoopArgs<T> &L)
     return ok;
 }
 
+// Writable page-table entries for [p, p + bytes) without changing a byte:
+// MADV_POPULATE_WRITE where the kernel has it (5.14+), else an atomic OR of
+// zero into one byte per page.
+static void populate_write(char *p, size_t bytes, const std::atomic<bool> &stop)
+{
+    const size_t page = 4096, chunk = 32u << 20;
+    char *b = (char *)((uintptr_t)p & ~(uintptr_t)(page - 1));
+    char *e = p + bytes;
+    bool useMadvise = true;
+    for (char *c = b; c < e && !stop.load(std::memory_order_relaxed); c += chunk) {
+        const size_t n = std::min<size_t>(chunk, (size_t)(e - c));
+#ifdef MADV_POPULATE_WRITE
+        if (useMadvise && madvise(c, n, MADV_POPULATE_WRITE) == 0)
+            continue;
+#endif
+        useMadvise = false;
+        for (char *q = std::max(c, p); q < c + n; q = (char *)(((uintptr_t)q & ~(uintptr_t)(page - 1)) + page))
+            __atomic_fetch_or(q, 0, __ATOMIC_RELAXED);
+    }
+}
+
+template <typename T>
+void Plan<T>::prefault_outputs(size_t end)
+{
+    if (!hostU_ || (opt_.outMode == 2 && stride_ == 0))
+        return;
+    const size_t slotBytes = denseCells_ * sizeof(T);
+    if (slotBytes < (16u << 20) || is_pinned_host(hostU_))
+        return;
+    // what download() will write: every slot, or (returned-slot hint, three
+    // rotating slots) only slot end % 3
+    size_t first = 0, count = numSlots_;
+    if (stride_ == 0 && opt_.outMode == 1) {
+        first = end % 3;
+        count = 1;
+    }
+    join_prefault();
+    prefaultStop_.store(false);
+    char *base = (char *)(hostU_ + first * hostSlotStride_);
+    const size_t bytes = (count - 1) * hostSlotStride_ * sizeof(T) + slotBytes;
+    prefault_ = std::thread([this, base, bytes] {
+        widen_helper_affinity();
+        populate_write(base, bytes, prefaultStop_);
+    });
+}
+
 template <typename T>
 void Plan<T>::download(void *u, void *receivers)
 {
+    NvtxRange nvtx("simwave_b200: drain");
+    join_prefault();
     const double t0 = wall();
     T *saveU = hostU_;
     if (u)

@@ -86,6 +86,8 @@ void cache_end_call();
 
 // true if [p, p+1) is page-locked host memory known to the CUDA driver
 bool is_pinned_host(const void *p);
+// helper threads: escape a one-core CPU mask inherited from a bound main thread
+void widen_helper_affinity();
 // memcpy split over a few threads (pageable <-> pinned staging copies)
 void parallel_memcpy(void *dst, const void *src, size_t bytes);
 
@@ -138,6 +140,12 @@ class PlanBase {
 public:
     virtual ~PlanBase() {}
     virtual void run(size_t begin, size_t end) = 0;
+    // Drop-in forward() only: fault in the pages of the caller's (pageable) `u`
+    // that the drain of [.., end] will write, on a helper thread, while the
+    // time loop runs.  simwave's Solver hands over a fresh np.zeros array: its
+    // pages do not exist yet, and taking the first-touch page faults inside
+    // the drain made it crawl at 5-8 GB/s.
+    virtual void prefault_outputs(size_t end) = 0;
     virtual void download(void *u, void *receivers) = 0;
     virtual void reset() = 0;
     virtual void slab_export(void *desc) = 0;

@@ -76,7 +76,8 @@ __global__ void rho_gradient_kernel(const __grid_constant__ StepArgs<T> a, T *__
 // flags[(s*tilesM + tm)*tilesF + tf] = 1 where q != 0 somewhere among the
 // interior points of tile (tm,tf) on plane s.  One block per (tile, plane);
 // blockIdx.z counts interior planes.
-static __global__ void qflag_kernel(Grid g, const float *__restrict__ q, int tileM, int tileF,
+template <typename T>
+__global__ void qflag_kernel(Grid g, const T *__restrict__ q, int tileM, int tileF,
                              unsigned char *__restrict__ flags)
 {
     const int s = g.r + blockIdx.z;
@@ -85,7 +86,7 @@ static __global__ void qflag_kernel(Grid g, const float *__restrict__ q, int til
     int any = 0;
     for (int idx = threadIdx.x; idx < tileM * tileF; idx += blockDim.x) {
         const int m = m0 + idx / tileF, f = f0 + idx % tileF;
-        if (m < m1 && f < f1 && q[g.at(s, m, f)] != 0.0f)
+        if (m < m1 && f < f1 && q[g.at(s, m, f)] != T(0))
             any = 1;
     }
     if (__syncthreads_or(any) && threadIdx.x == 0)

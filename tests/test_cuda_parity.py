@@ -187,6 +187,45 @@ def test_fast_math_within_tolerance(shape, order, density, steps, monkeypatch):
     assert_close(a, b)
 
 
+def as_float64(p):
+    """The same problem with every float32 array widened (identical inputs)."""
+    q = problems.clone(p)
+    for k, v in list(q.items()):
+        if isinstance(v, np.ndarray) and v.dtype == np.float32:
+            q[k] = v.astype(np.float64)
+        elif isinstance(v, np.float32):
+            q[k] = np.float64(v)
+    return q
+
+
+@pytest.mark.parametrize("shape,order,steps", [((200, 210), 8, 1500),
+                                               ((56, 60, 64), 8, 900)])
+def test_fast_math_long_run_stays_at_the_float32_noise_floor(shape, order, steps,
+                                                             monkeypatch):
+    """Long loops (per-point random velocity: the worst case for rounding
+    noise).  Two float32 evaluations of the same recursion drift apart like the
+    sum of their rounding noises, so the distance to the reference's float32
+    kernel alone says little; measured against the reference's float64 run on
+    the same inputs, FAST mode must be as accurate as the reference's own
+    float32 kernel (within 25 %), and stay under the stated 1e-4 of the
+    float32 kernel."""
+    nbl = ((0, 6),) + ((5, 5),) * (len(shape) - 1)
+    p = problems.make_problem(shape=shape, space_order=order, timesteps=steps,
+                              seed=3, nbl=nbl)
+    ref32, ref64 = problems.clone(p), as_float64(p)
+    oracle.forward(ref32)
+    oracle.forward(ref64)
+    monkeypatch.setenv("SIMWAVE_CUDA_MATH", "fast")
+    b = problems.clone(p)
+    cuda_forward(b)
+    for key in ("u", "receivers"):
+        floor = rel_l2(ref32[key], ref64[key])
+        to_truth = rel_l2(b[key], ref64[key])
+        to_ref32 = rel_l2(b[key], ref32[key])
+        assert to_truth <= 1.25 * floor, (key, to_truth, floor)
+        assert to_ref32 <= 1e-4, (key, to_ref32)
+
+
 def test_nonzero_initial_fields_are_honoured():
     """`u` is in/out: slots 0..2 may carry an initial condition."""
     p = problems.make_problem(shape=(36, 40), space_order=4, timesteps=15,
@@ -323,11 +362,12 @@ def test_u_saving(dimension, density, stride):
 # tiled 3D kernel: every radius and tile configuration against the plain kernel
 # ---------------------------------------------------------------------------
 def _tiled_vs_plain(order, tile, monkeypatch, shape=(37, 75, 150), steps=6,
-                    bc=(2, 1, 2, 1, 2, 1), math="strict", density=False):
+                    bc=(2, 1, 2, 1, 2, 1), math="strict", density=False,
+                    dtype=np.float32):
     r = order // 2
     p = problems.make_problem(
         shape=shape, space_order=order, timesteps=steps, bc=bc, seed=order,
-        density=density,
+        density=density, dtype=dtype,
         nbl=((0, 3), (2, 2), (3, 2)), num_sources=2, src_radius=min(4, r + 1),
         num_receivers=6, rec_radius=2)
     monkeypatch.setenv("SIMWAVE_CUDA_MATH", math)
@@ -363,6 +403,37 @@ def test_tiled_variable_density_every_radius(order, math, monkeypatch):
                                        density=True)
         assert np.array_equal(plain["u"], tiled["u"]), (order, cfg)
         assert np.array_equal(plain["receivers"], tiled["receivers"])
+
+
+@pytest.mark.parametrize("math", ["strict", "fast"])
+@pytest.mark.parametrize("order", [2, 4, 6, 8, 10, 12, 14, 16, 18, 20])
+def test_tiled_float64_kernel_every_radius(order, math, monkeypatch):
+    """float64 3D (what simwave's own overthrust benchmark script runs): the
+    tiled kernel of sw_step_tiled3d64.cuh against the plain kernel, bit for
+    bit, on a grid whose extents are no multiples of the tile, with damping
+    layers, mixed boundary conditions and several z-chunk lengths."""
+    for zchunk in (0, 7, 1000):
+        plain, tiled = _tiled_vs_plain(order, "0:%d" % zchunk, monkeypatch,
+                                       shape=(45, 61, 107), math=math,
+                                       dtype=np.float64)
+        assert np.array_equal(plain["u"], tiled["u"]), (order, zchunk)
+        assert np.array_equal(plain["receivers"], tiled["receivers"])
+
+
+@pytest.mark.parametrize("bc", [(2, 2, 2, 2, 2, 2), (1, 1, 1, 1, 1, 1),
+                                (0, 2, 1, 0, 2, 1), (0, 0, 0, 0, 0, 0)])
+def test_tiled_float64_kernel_boundaries_and_oracle(bc, monkeypatch):
+    """float64 3D through the tiled kernel against the CPU oracle (strict: bit
+    for bit), every boundary mix, fused and separate boundary passes."""
+    p = problems.make_problem(shape=(44, 70, 99), space_order=8, timesteps=25,
+                              bc=bc, seed=21, dtype=np.float64,
+                              nbl=((0, 5), (4, 4), (4, 3)))
+    a, b = run_pair(p, {"SIMWAVE_CUDA_MATH": "strict"}, monkeypatch)
+    assert_identical(a, b)
+    monkeypatch.setenv("SIMWAVE_CUDA_BC", "separate")
+    c = problems.clone(p)
+    cuda_forward(c)
+    assert np.array_equal(a["u"], c["u"])
 
 
 def test_tiled_variable_density_matches_oracle():

@@ -17,8 +17,8 @@ t0=$(date +%s)
 timeout 900 python bench.py --impl reference > gpurun_out/${R}_bench_ref_n1.json 2> gpurun_out/${R}_bench_ref_n1.err
 echo "reference arm wall $(( $(date +%s) - t0 )) s" | tee -a gpurun_out/${R}_bench_n1.wall
 cat gpurun_out/${R}_bench_ref_n1.json | cut -c1-600
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_c3.csv python bench.py --timesteps 40 --steps 1 --warmup 1 --no-cpu --no-e2e --no-slab --no-survey --no-2d --no-api > gpurun_out/${R}_bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:step3d_tiled -s 30 -c 1 -o gpurun_out/${R}_prof_c3 -f python bench.py --timesteps 40 --steps 1 --warmup 1 --no-cpu --no-e2e --no-slab --no-survey --no-2d --no-api > gpurun_out/${R}_ncu_c3.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_c3.csv python bench.py --timesteps 40 --steps 1 --warmup 1 --no-cpu --no-e2e --no-slab --no-survey --no-2d --no-api --no-f64 > gpurun_out/${R}_bench_under_ncu.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:step3d_tiled -s 30 -c 1 -o gpurun_out/${R}_prof_c3 -f python bench.py --timesteps 40 --steps 1 --warmup 1 --no-cpu --no-e2e --no-slab --no-survey --no-2d --no-api --no-f64 > gpurun_out/${R}_ncu_c3.log 2>&1
 tail -2 gpurun_out/${R}_ncu_c3.log
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:step3d_tiled -s 3 -c 1 -o gpurun_out/${R}_prof_c4 -f python tools/sweep.py --workload slab_3d --kw planes_per_gpu=512 --timesteps 6 --cfgs 5 --math fast --repeat 1 --no-simple > gpurun_out/${R}_ncu_c4.log 2>&1
 tail -2 gpurun_out/${R}_ncu_c4.log

@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--kw", action="append", default=[],
                     help="extra integer keyword of the workload builder, key=value")
     ap.add_argument("--no-simple", action="store_true", help="skip the plain kernel")
+    ap.add_argument("--dtype", default=None, choices=["f32", "f64"],
+                    help="precision of the workload (builders that take a dtype)")
     ap.add_argument("--prefetch", default="",
                     help="comma list of SIMWAVE_CUDA_PREFETCH distances to cross with the tiles")
     args = ap.parse_args()
@@ -37,6 +39,9 @@ def main():
     kwargs = {"timesteps": args.timesteps}
     if args.space_order:
         kwargs["space_order"] = args.space_order
+    if args.dtype:
+        import numpy as np
+        kwargs["dtype"] = np.float32 if args.dtype == "f32" else np.float64
     for kv in args.kw:
         k, v = kv.split("=")
         kwargs[k] = int(v)

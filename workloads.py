@@ -159,9 +159,11 @@ def _layered_3d(shape, vmin, vmax, seed, step_axis=2):
     return np.clip(vel, vmin, vmax).astype(np.float32)
 
 
-def overthrust_3d(space_order=8, timesteps=None, seed=2):
+def overthrust_3d(space_order=8, timesteps=None, seed=2, dtype=np.float32):
     """C3: Overthrust-shaped 207 x 801 x 801 model, no damping layer
-    (benchmark/overthrust_3D.py:77-114)."""
+    (benchmark/overthrust_3D.py:77-114).  The bench line is float32 (what
+    north_star asks for); the reference's script itself builds a float64 model
+    (overthrust_3D.py:82), which ``dtype=np.float64`` reproduces."""
     vel = _layered_3d((207, 801, 801), 2179.0, 6000.0, seed)
     return _assemble(
         vel, None, ((0, 0),) * 3, (20.0, 20.0, 20.0), space_order,
@@ -169,7 +171,7 @@ def overthrust_3d(space_order=8, timesteps=None, seed=2):
          "null_dirichlet", "null_dirichlet"),
         [(20.0, 8000.0, 8000.0)],
         [(20.0, 8000.0, 20.0 * i) for i in range(800)],
-        1, 8.0, 4.0, timesteps, name="overthrust_3d")
+        1, 8.0, 4.0, timesteps, dtype=dtype, name="overthrust_3d")
 
 
 def variable_density_3d(n=1024, space_order=16, timesteps=200, nz=None):

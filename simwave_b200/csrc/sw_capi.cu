@@ -243,6 +243,7 @@ static double run_forward_slabs(const simwave_problem &pb, size_t begin, size_t 
             q.receivers = traces[k].data();
 
             std::unique_ptr<PlanBase> plan = make_plan(q, opt);
+            plan->prefault_outputs(end);      // this slab's part of the caller's `u`
             plan->slab_peer(&peers[k]);
             if (!meet.meet())
                 return;

@@ -1911,11 +1911,11 @@ void Plan<T>::prefault_outputs(size_t end)
     }
     join_prefault();
     prefaultStop_.store(false);
-    char *base = (char *)(hostU_ + first * hostSlotStride_);
-    const size_t bytes = (count - 1) * hostSlotStride_ * sizeof(T) + slotBytes;
-    prefault_ = std::thread([this, base, bytes] {
+    // slot by slot: a slab plan's slots are windows of the caller's larger array
+    prefault_ = std::thread([this, first, count, slotBytes] {
         widen_helper_affinity();
-        populate_write(base, bytes, prefaultStop_);
+        for (size_t s = first; s < first + count; s++)
+            populate_write((char *)(hostU_ + s * hostSlotStride_), slotBytes, prefaultStop_);
     });
 }
 

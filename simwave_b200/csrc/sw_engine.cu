@@ -638,8 +638,8 @@ static const TiledLaunchFn kTiledLaunch[kMaxRadius + 1] = {
     tiled3d_launch_r5, tiled3d_launch_r6, tiled3d_launch_r7, tiled3d_launch_r8,
     tiled3d_launch_r9, tiled3d_launch_r10};
 
-typedef bool (*Tiled64QueryFn)(TiledInfo *);
-typedef bool (*Tiled64LaunchFn)(int, const StepArgs<double> &, const StepMaps &,
+typedef bool (*Tiled64QueryFn)(bool, int, TiledInfo *);
+typedef bool (*Tiled64LaunchFn)(bool, int, const StepArgs<double> &, const StepMaps &,
                                 const unsigned char *, int, cudaStream_t);
 static const Tiled64QueryFn kTiled64Query[kMaxRadius + 1] = {
     nullptr, tiled3d64_query_r1, tiled3d64_query_r2, tiled3d64_query_r3, tiled3d64_query_r4,
@@ -1364,9 +1364,9 @@ void Plan<T>::choose_tiling()
     useTiled_ = false;
     constexpr bool kF32 = std::is_same<T, float>::value;
     {
-        // float32: every 3D variant but the stride-quirk case; float64:
-        // constant density (sw_step_tiled3d64.cuh)
-        if (opt_.simple || ndim_ != 3 || (varden_ && (args_.quirk || !kF32)))
+        // every 3D variant but the stride-quirk case (float64:
+        // sw_step_tiled3d64.cuh)
+        if (opt_.simple || ndim_ != 3 || (varden_ && args_.quirk))
             return;
         const int r = g_.r;
         // default configuration, overridable as SIMWAVE_CUDA_TILE=<cfg>[:<zchunk>]
@@ -1394,7 +1394,7 @@ void Plan<T>::choose_tiling()
                 throw Error("SIMWAVE_CUDA_TILE: no such tile configuration");
         } else {
             cfg = 0;
-            kTiled64Query[r](&tiledInfo_);
+            kTiled64Query[r](varden_, opt_.math, &tiledInfo_);
         }
         if (tiledInfo_.smemBytes > maxSmem)
             return;   // plain kernel
@@ -1519,8 +1519,14 @@ void Plan<T>::launch_step(const StepArgs<T> &a)
             maps.prev = field_map(a.prev, false);
             maps.c0 = field_map(a.c0, false);
             maps.q = field_map(a.q, false);
-            if (!kTiled64Launch[g_.r](opt_.math, a, maps, model_->qflags.as<unsigned char>(),
-                                      zChunk_, stream_))
+            if (varden_) {
+                maps.rho = field_map(a.rho, false);
+                maps.frF = field_map(field_base(model_->frF), false);
+                maps.frM = field_map(field_base(model_->frM), false);
+                maps.frS = field_map(field_base(model_->frS), false);
+            }
+            if (!kTiled64Launch[g_.r](varden_, opt_.math, a, maps,
+                                      model_->qflags.as<unsigned char>(), zChunk_, stream_))
                 throw Error("tiled float64 kernel vanished");
             check_launch("tiled float64 step kernel");
             return;

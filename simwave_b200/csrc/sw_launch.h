@@ -95,11 +95,12 @@ struct StepMaps {
 SW_DECL_TILED(1) SW_DECL_TILED(2) SW_DECL_TILED(3) SW_DECL_TILED(4) SW_DECL_TILED(5)
 SW_DECL_TILED(6) SW_DECL_TILED(7) SW_DECL_TILED(8) SW_DECL_TILED(9) SW_DECL_TILED(10)
 #undef SW_DECL_TILED
-// float64, constant density (sw_step_tiled3d64.cuh)
+// float64 (sw_step_tiled3d64.cuh)
 #define SW_DECL_TILED64(R)                                                            \
-    bool tiled3d64_query_r##R(TiledInfo *info);                                       \
-    bool tiled3d64_launch_r##R(int math, const StepArgs<double> &a, const StepMaps &maps, \
-                               const unsigned char *qflags, int zChunk, cudaStream_t stream);
+    bool tiled3d64_query_r##R(bool varden, int math, TiledInfo *info);                \
+    bool tiled3d64_launch_r##R(bool varden, int math, const StepArgs<double> &a,      \
+                               const StepMaps &maps, const unsigned char *qflags,     \
+                               int zChunk, cudaStream_t stream);
 SW_DECL_TILED64(1) SW_DECL_TILED64(2) SW_DECL_TILED64(3) SW_DECL_TILED64(4) SW_DECL_TILED64(5)
 SW_DECL_TILED64(6) SW_DECL_TILED64(7) SW_DECL_TILED64(8) SW_DECL_TILED64(9) SW_DECL_TILED64(10)
 #undef SW_DECL_TILED64

@@ -7,6 +7,8 @@
 // the tiled kernels are validated against.
 #pragma once
 
+#include <type_traits>
+
 #include "sw_math.cuh"
 
 namespace sw {
@@ -103,10 +105,20 @@ __device__ __forceinline__ long long dense_shift(const Grid &g, int denseNx, int
 // / density at signed offsets along an axis: C() centre, F(k), M(k), S(k), and
 // M1(k) = the neighbour the FIRST derivative along M uses (it differs from M(k)
 // only under the bug-compatible strides of variable_density/3d/wave.c:185-186).
+// A density accessor may instead carry the three first derivatives of the
+// density already summed (rho_gradient_kernel: same ring order and roundings;
+// in FAST mode already weighted by 1 / (4 h^2 rho)): it then declares
+// `static constexpr bool kDerivatives = true` and offers frF() / frM() / frS().
+template <class D, class = void>
+struct has_derivatives : std::false_type {};
+template <class D>
+struct has_derivatives<D, std::void_t<decltype(D::kDerivatives)>> : std::true_type {};
+
 template <typename T, int NDIM, bool VARDEN, int R, int MATH, class U, class D>
 __device__ __forceinline__ T value_from_neighbours(const StepArgs<T> &a, const U &u, const D &d,
                                                    T prevv, T c0v, T qv)
 {
+    constexpr bool kPre = VARDEN && has_derivatives<D>::value;
     const T uc = u.C();
 
     // second derivatives: c[0]*u + sum_ir c[ir]*(u[+ir] + u[-ir]), per axis
@@ -130,18 +142,26 @@ __device__ __forceinline__ T value_from_neighbours(const StepArgs<T> &a, const U
         if (VARDEN) {
             if constexpr (!SPLIT)
                 fpF = ring_diff<T, MATH>(fpF, a.c1[ir], u.F(ir), u.F(-ir));
-            frF = ring_diff<T, MATH>(frF, a.c1[ir], d.F(ir), d.F(-ir));
             fpM = ring_diff<T, MATH>(fpM, a.c1[ir], u.M1(ir), u.M1(-ir));
-            frM = ring_diff<T, MATH>(frM, a.c1[ir], d.M1(ir), d.M1(-ir));
-            if (NDIM == 3) {
+            if (NDIM == 3)
                 fpS = ring_diff<T, MATH>(fpS, a.c1[ir], u.S(ir), u.S(-ir));
-                frS = ring_diff<T, MATH>(frS, a.c1[ir], d.S(ir), d.S(-ir));
+            if constexpr (!kPre) {
+                frF = ring_diff<T, MATH>(frF, a.c1[ir], d.F(ir), d.F(-ir));
+                frM = ring_diff<T, MATH>(frM, a.c1[ir], d.M1(ir), d.M1(-ir));
+                if (NDIM == 3)
+                    frS = ring_diff<T, MATH>(frS, a.c1[ir], d.S(ir), d.S(-ir));
             }
         }
     }
 
     T lap = acc.laplacian(a);
-    if (VARDEN) {
+    if constexpr (kPre) {
+        if (MATH == MATH_STRICT)
+            lap = density_term<T, NDIM>(lap, fpS, d.frS(), fpM, d.frM(), fpF, d.frF(), a.four_h2,
+                                        d.C());
+        else
+            lap = fast_density_term<T, NDIM>(lap, fpS, d.frS(), fpM, d.frM(), fpF, d.frF());
+    } else if (VARDEN) {
         if (MATH == MATH_STRICT) {
             lap = density_term<T, NDIM>(lap, fpS, frS, fpM, frM, fpF, frF, a.four_h2, d.C());
         } else {

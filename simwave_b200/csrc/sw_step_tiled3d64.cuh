@@ -1,4 +1,4 @@
-// Tiled 3D step kernel for float64 (constant density) on sm_100a.
+// Tiled 3D step kernel for float64 (constant and variable density) on sm_100a.
 //
 // simwave's own 3D benchmark script builds its model in float64
 // (benchmark/overthrust_3D.py:82), so the double-precision variant is what an
@@ -18,17 +18,21 @@
 // itself is simply value_from_neighbours<double, 3, ...> -- the one statement
 // of the reference's section-1 arithmetic every kernel goes through -- on a
 // neighbour accessor over the ring and the queue: bit-identical to the plain
-// kernel in either math mode by construction.
+// kernel in either math mode by construction.  Variable density: as in the
+// float32 kernel the three first derivatives of the density (constant in time,
+// rho_gradient_kernel) arrive as halo-free stream tiles next to u_prev, c0, q.
 #pragma once
 
 #include "sw_step_tiled3d.cuh"
 
 namespace sw {
 
-template <int R, int TX, int TY, int PF, int PS>
+template <int R, int TX, int TY, int PF, int PS, bool VARDEN = false, bool RHO = VARDEN>
 struct Tile3D64 {
     static constexpr int VW = 2;                     // points per thread along F
-    static constexpr int NSTR = 3;                   // prev | c0 | q
+    // stream tiles of one stage: prev | c0 | q [| frF | frM | frS [| rho]] (rho
+    // itself only in STRICT mode: FAST folds 1/rho into the derivatives)
+    static constexpr int NSTR = VARDEN ? (RHO ? 7 : 6) : 3;
     static constexpr int RP = (R + 1) / 2 * 2;       // F halo rounded to a double2
     static constexpr int BX = TY;                    // rows (M) per tile
     static constexpr int BY = TX * VW;               // columns (F) per tile
@@ -66,13 +70,25 @@ struct Tile64Neighbours {
     __device__ __forceinline__ double S(int k) const { return q[k]; }
 };
 
-template <int R, int TX, int TY, int PF, int PS, int MATH, int MINB>
+// the density of one point as the tiled kernels stream it: its value and its
+// three first derivatives, summed once per run by rho_gradient_kernel
+struct Tile64Density {
+    static constexpr bool kDerivatives = true;
+    double rho, gF, gM, gS;
+    __device__ __forceinline__ double C() const { return rho; }
+    __device__ __forceinline__ double frF() const { return gF; }
+    __device__ __forceinline__ double frM() const { return gM; }
+    __device__ __forceinline__ double frS() const { return gS; }
+};
+
+template <int R, int TX, int TY, int PF, int PS, int MATH, int MINB, bool VARDEN>
 __global__ void __launch_bounds__(TX *TY + 32, MINB)
 step3d_tiled64_kernel(const __grid_constant__ StepArgs<double> a,
                       const __grid_constant__ StepMaps maps,
                       const unsigned char *__restrict__ qflags, int zChunk)
 {
-    using TL = Tile3D64<R, TX, TY, PF, PS>;
+    constexpr bool RHO = VARDEN && MATH == MATH_STRICT;
+    using TL = Tile3D64<R, TX, TY, PF, PS, VARDEN, RHO>;
     constexpr int RP = TL::RP, BYH = TL::BYH, NS = TL::NS, NT = TL::NT;
     constexpr int Q = 2 * R + 1;
     constexpr int NCW = TL::CONSUMERS / 32;
@@ -127,12 +143,21 @@ step3d_tiled64_kernel(const __grid_constant__ StepArgs<double> a,
                 mbar_wait(&emptyStr[st], ((j / NT) - 1) & 1);
             double *dst = streams + st * TL::STAGE_ELEMS;
             stageHasQ[st] = hasQ;
-            mbar_expect_tx(&fullStr[st], (hasQ ? 3 : 2) * TL::STR_BYTES);
-            tma_load_3d(dst, &maps.prev, &fullStr[st], g.lpad + f0, m0, z0 + j);
-            tma_load_3d(dst + TL::STR_ELEMS, &maps.c0, &fullStr[st], g.lpad + f0, m0, z0 + j);
+            mbar_expect_tx(&fullStr[st], ((hasQ ? 3 : 2) + (TL::NSTR - 3)) * TL::STR_BYTES);
+            auto load = [&](int tile, const CUtensorMap *map) {
+                tma_load_3d(dst + tile * TL::STR_ELEMS, map, &fullStr[st], g.lpad + f0, m0, z0 + j);
+            };
+            load(0, &maps.prev);
+            load(1, &maps.c0);
             if (hasQ)
-                tma_load_3d(dst + 2 * TL::STR_ELEMS, &maps.q, &fullStr[st], g.lpad + f0, m0,
-                            z0 + j);
+                load(2, &maps.q);
+            if (VARDEN) {
+                load(3, &maps.frF);
+                load(4, &maps.frM);
+                load(5, &maps.frS);
+                if (RHO)
+                    load(6, &maps.rho);
+            }
         };
         const int ahead = min(max(maps.prefetch, 0), 32);
         auto prefetch_plane = [&](int j, int hasQ) {
@@ -141,6 +166,13 @@ step3d_tiled64_kernel(const __grid_constant__ StepArgs<double> a,
             tma_prefetch_3d(&maps.c0, g.lpad + f0, m0, z0 + j);
             if (hasQ)
                 tma_prefetch_3d(&maps.q, g.lpad + f0, m0, z0 + j);
+            if (VARDEN) {
+                tma_prefetch_3d(&maps.frF, g.lpad + f0, m0, z0 + j);
+                tma_prefetch_3d(&maps.frM, g.lpad + f0, m0, z0 + j);
+                tma_prefetch_3d(&maps.frS, g.lpad + f0, m0, z0 + j);
+                if (RHO)
+                    tma_prefetch_3d(&maps.rho, g.lpad + f0, m0, z0 + j);
+            }
         };
         auto flag_mask = [&](int b) -> unsigned {
             int flag = 0;
@@ -264,8 +296,21 @@ step3d_tiled64_kernel(const __grid_constant__ StepArgs<double> a,
         {
             const Tile64Neighbours<R, BYH> n0{w + RP, ctr + srow * BYH + scol, qv[0] + R};
             const Tile64Neighbours<R, BYH> n1{w + RP + 1, ctr + srow * BYH + scol + 1, qv[1] + R};
-            out[0] = value_from_neighbours<double, 3, false, R, MATH>(a, n0, n0, pv.x, cv.x, qd.x);
-            out[1] = value_from_neighbours<double, 3, false, R, MATH>(a, n1, n1, pv.y, cv.y, qd.y);
+            if constexpr (VARDEN) {
+                auto tile2 = [&](int t) {
+                    return *reinterpret_cast<const double2 *>(sPrev + t * TL::STR_ELEMS + off);
+                };
+                const double2 gF = tile2(3), gM = tile2(4), gS = tile2(5);
+                double2 rv = make_double2(1.0, 1.0);
+                if (RHO)
+                    rv = tile2(6);
+                const Tile64Density d0{rv.x, gF.x, gM.x, gS.x}, d1{rv.y, gF.y, gM.y, gS.y};
+                out[0] = value_from_neighbours<double, 3, true, R, MATH>(a, n0, d0, pv.x, cv.x, qd.x);
+                out[1] = value_from_neighbours<double, 3, true, R, MATH>(a, n1, d1, pv.y, cv.y, qd.y);
+            } else {
+                out[0] = value_from_neighbours<double, 3, false, R, MATH>(a, n0, n0, pv.x, cv.x, qd.x);
+                out[1] = value_from_neighbours<double, 3, false, R, MATH>(a, n1, n1, pv.y, cv.y, qd.y);
+            }
         }
 
         release(&emptyCur[slotC]);

@@ -420,6 +420,27 @@ def test_tiled_float64_kernel_every_radius(order, math, monkeypatch):
         assert np.array_equal(plain["receivers"], tiled["receivers"])
 
 
+@pytest.mark.parametrize("math", ["strict", "fast"])
+@pytest.mark.parametrize("order", [2, 4, 8, 12, 16, 20])
+def test_tiled_float64_variable_density_every_radius(order, math, monkeypatch):
+    """float64 3D with a density model (streamed density derivatives, as in
+    the float32 kernel) against the plain kernel, bit for bit, nx == ny."""
+    for zchunk in (0, 9):
+        plain, tiled = _tiled_vs_plain(order, "0:%d" % zchunk, monkeypatch,
+                                       shape=(45, 88, 88), math=math,
+                                       density=True, dtype=np.float64)
+        assert np.array_equal(plain["u"], tiled["u"]), (order, zchunk)
+        assert np.array_equal(plain["receivers"], tiled["receivers"])
+
+
+def test_tiled_float64_variable_density_matches_oracle(monkeypatch):
+    p = problems.make_problem(shape=(46, 72, 72), space_order=8, density=True,
+                              timesteps=25, seed=14, smooth_density=True,
+                              dtype=np.float64, nbl=((0, 5), (4, 4), (4, 4)))
+    a, b = run_pair(p, {"SIMWAVE_CUDA_MATH": "strict"}, monkeypatch)
+    assert_identical(a, b)
+
+
 @pytest.mark.parametrize("bc", [(2, 2, 2, 2, 2, 2), (1, 1, 1, 1, 1, 1),
                                 (0, 2, 1, 0, 2, 1), (0, 0, 0, 0, 0, 0)])
 def test_tiled_float64_kernel_boundaries_and_oracle(bc, monkeypatch):

@@ -328,17 +328,31 @@ step3d_tiled_kernel(const __grid_constant__ StepArgs<float> a,
         const long long tilesPerPlane = (long long)gridDim.x * gridDim.y;
         const unsigned char *myFlags =
             qflags + (long long)blockIdx.y * gridDim.x + blockIdx.x;
+#ifdef SW_EXP_NOMEM
+        // development probe (never built by default): every CTA loads the same
+        // few tiles, which stay in L2 -- the SM side of the kernel alone
+#define SW_PROBE_F R
+#define SW_PROBE_M R
+#define SW_PROBE_Z(z) (R + ((z) & 15))
+#else
+#define SW_PROBE_F f0
+#define SW_PROBE_M m0
+#define SW_PROBE_Z(z) (z)
+#endif
         auto issue_cur = [&](int l) {
             const int slot = l % NS;
             if (l >= NS)
                 mbar_wait(&emptyCur[slot], ((l / NS) - 1) & 1);
             mbar_expect_tx(&fullCur[slot], TL::BOX_BYTES);
             tma_load_3d(ring + slot * TL::SLOT_FLOATS, &maps.cur, &fullCur[slot],
-                        g.lpad + f0 - RP, m0 - R, z0 - R + l);
+                        g.lpad + SW_PROBE_F - RP, SW_PROBE_M - R, SW_PROBE_Z(z0 - R + l));
         };
         auto load_stream = [&](float *dst, const CUtensorMap *map, uint64_t *bar, int j) {
-            tma_load_3d(dst, map, bar, g.lpad + f0, m0, z0 + j);
+            tma_load_3d(dst, map, bar, g.lpad + SW_PROBE_F, SW_PROBE_M, SW_PROBE_Z(z0 + j));
         };
+#undef SW_PROBE_F
+#undef SW_PROBE_M
+#undef SW_PROBE_Z
         auto issue_streams = [&](int j, int hasQ) {
             const int st = j % NT;
             if (j >= NT)

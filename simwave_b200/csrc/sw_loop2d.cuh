@@ -42,9 +42,14 @@ constexpr int kLoop2dGroups = kLoop2dThreads / (kLoop2dCols / 4);   // row group
 template <typename T, int R, bool VARDEN>
 struct Loop2dShape {
     static constexpr bool F32 = sizeof(T) == 4;
+    // a strip is one 128-bit vector wide: 4 floats or 2 doubles
+    static constexpr int VW = 16 / (int)sizeof(T);
     static constexpr int ROWS =
-        F32 ? (!VARDEN ? (R <= 5 ? 1 : 0) : (R <= 2 ? 1 : 0)) : (!VARDEN ? (R <= 1 ? 1 : 0) : 0);
+        F32 ? (!VARDEN ? (R <= 5 ? 1 : 0) : (R <= 2 ? 1 : 0)) : (!VARDEN ? (R <= 4 ? 1 : 0) : (R <= 2 ? 1 : 0));
     static constexpr int TILE_ROWS = kLoop2dGroups * (ROWS ? ROWS : 1);
+    // columns of a tile: a warp covers one row of strips (the one-point-per-
+    // thread path keeps 128 columns)
+    static constexpr int COLS = ROWS ? 32 * VW : kLoop2dCols;
     // two-wide float32 arithmetic for the four points of a strip (FAST mode)
     static constexpr bool PACKED = F32 && !VARDEN && ROWS == 1;
     // threads of a CTA of the tile-resident loop (one CTA per SM): as many warps
@@ -79,14 +84,29 @@ __device__ __forceinline__ void store4(double *p, const double v[4])
     *reinterpret_cast<double2 *>(p + 2) = make_double2(v[2], v[3]);
 }
 
-// Neighbourhood of a strip of ROWS x 4 points (rows m0.., columns f0..f0+3)
-// held in registers: `col` = my four columns over rows m0-R .. m0+ROWS+R-1
-// (vertically adjacent points share them), `side` = the RP elements left and
-// right of my columns on my own rows.
+// one 128-bit vector of elements: 4 floats or 2 doubles (16-byte aligned:
+// f == r mod VW in the pitched layout)
+__device__ __forceinline__ void loadv(const float *p, float out[4]) { load4<float>(p, out); }
+__device__ __forceinline__ void loadv(const double *p, double out[2])
+{
+    const double2 a = *reinterpret_cast<const double2 *>(p);
+    out[0] = a.x; out[1] = a.y;
+}
+__device__ __forceinline__ void storev(float *p, const float v[4]) { store4(p, v); }
+__device__ __forceinline__ void storev(double *p, const double v[2])
+{
+    *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+}
+
+// Neighbourhood of a strip of ROWS x VW points (rows m0.., columns f0..f0+VW-1;
+// VW = one 128-bit vector) held in registers: `col` = my columns over rows
+// m0-R .. m0+ROWS+R-1 (vertically adjacent points share them), `side` = the RP
+// elements left and right of my columns on my own rows.
 template <typename T, int R, int ROWS>
 struct Strip {
-    static constexpr int RP = (R + 3) / 4 * 4;
-    T col[ROWS + 2 * R][4];
+    static constexpr int VW = 16 / (int)sizeof(T);
+    static constexpr int RP = (R + VW - 1) / VW * VW;
+    T col[ROWS + 2 * R][VW];
     T side[ROWS][2][RP];
 
     __device__ __forceinline__ void load(const Grid &g, const T *field, int m0, int f0,
@@ -94,22 +114,25 @@ struct Strip {
     {
 #pragma unroll
         for (int j = 0; j < ROWS + 2 * R; j++) {
-            if (j < rowsValid + 2 * R)
-                load4<T>(field + g.at(0, m0 - R + j, f0), col[j]);
-            else
-                col[j][0] = col[j][1] = col[j][2] = col[j][3] = T(0);
+            if (j < rowsValid + 2 * R) {
+                loadv(field + g.at(0, m0 - R + j, f0), col[j]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < VW; e++)
+                    col[j][e] = T(0);
+            }
         }
 #pragma unroll
         for (int i = 0; i < ROWS; i++)
 #pragma unroll
-            for (int b = 0; b < RP / 4; b++) {
+            for (int b = 0; b < RP / VW; b++) {
                 if (i < rowsValid) {
-                    load4<T>(field + g.at(0, m0 + i, f0 - RP + 4 * b), &side[i][0][4 * b]);
-                    load4<T>(field + g.at(0, m0 + i, f0 + 4 + 4 * b), &side[i][1][4 * b]);
+                    loadv(field + g.at(0, m0 + i, f0 - RP + VW * b), &side[i][0][VW * b]);
+                    loadv(field + g.at(0, m0 + i, f0 + VW + VW * b), &side[i][1][VW * b]);
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 4; e++)
-                        side[i][0][4 * b + e] = side[i][1][4 * b + e] = T(0);
+                    for (int e = 0; e < VW; e++)
+                        side[i][0][VW * b + e] = side[i][1][VW * b + e] = T(0);
                 }
             }
     }
@@ -121,14 +144,15 @@ struct StripNeighbours {
     const Strip<T, R, ROWS> &t;
     int i, c;
     static constexpr int RP = Strip<T, R, ROWS>::RP;
+    static constexpr int VW = Strip<T, R, ROWS>::VW;
     __device__ __forceinline__ T C() const { return t.col[i + R][c]; }
     __device__ __forceinline__ T F(int k) const
     {
         const int idx = c + k;
         if (idx < 0)
             return t.side[i][0][RP + idx];
-        if (idx > 3)
-            return t.side[i][1][idx - 4];
+        if (idx > VW - 1)
+            return t.side[i][1][idx - VW];
         return t.col[i + R][idx];
     }
     __device__ __forceinline__ T M(int k) const { return t.col[i + R + k][c]; }
@@ -234,12 +258,14 @@ loop2d_persistent_kernel(const __grid_constant__ LoopArgs<T> L)
 {
     constexpr int ROWS = Loop2dShape<T, R, VARDEN>::ROWS;
     constexpr int TILE_ROWS = Loop2dShape<T, R, VARDEN>::TILE_ROWS;
+    constexpr int VW = Loop2dShape<T, R, VARDEN>::VW;
+    constexpr int COLS = Loop2dShape<T, R, VARDEN>::COLS;
     const StepArgs<T> &a = L.a;
     const Grid &g = a.g;
 
     const int nFi = g.nF - 2 * R, nMi = g.nM - 2 * R;   // interior extents
     const int lastF = g.nF - R - 1, lastM = g.nM - R - 1;
-    const int tilesF = (nFi + kLoop2dCols - 1) / kLoop2dCols;
+    const int tilesF = (nFi + COLS - 1) / COLS;
     const int tilesM = (nMi + TILE_ROWS - 1) / TILE_ROWS;
     const long long tiles = (long long)tilesF * tilesM;
     const int warpsPerBlock = blockDim.x >> 5;
@@ -336,32 +362,32 @@ loop2d_persistent_kernel(const __grid_constant__ LoopArgs<T> L)
         // stencil: tiles of TILE_ROWS x kLoop2dCols points, block-strided
         for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
             if constexpr (ROWS > 0) {
-                // a thread owns ROWS x 4 points; operands through 128-bit loads
-                const int f0 = R + (int)(t % tilesF) * kLoop2dCols + 4 * (threadIdx.x & 31);
+                // a thread owns ROWS x VW points; operands through 128-bit loads
+                const int f0 = R + (int)(t % tilesF) * COLS + VW * (threadIdx.x & 31);
                 const int m0 = R + (int)(t / tilesF) * TILE_ROWS + (threadIdx.x >> 5) * ROWS;
                 const int rowsValid = min(ROWS, lastM - m0 + 1);
-                const int colsValid = min(4, lastF - f0 + 1);
+                const int colsValid = min(VW, lastF - f0 + 1);
                 if (rowsValid <= 0 || colsValid <= 0)
                     continue;
                 Strip<T, R, ROWS> su, sd;
                 su.load(g, cur, m0, f0, rowsValid);
                 if (VARDEN)
                     sd.load(g, a.rho, m0, f0, rowsValid);
-                T out[ROWS][4];
+                T out[ROWS][VW];
 #pragma unroll
                 for (int i = 0; i < ROWS; i++) {
                     if (i >= rowsValid)
                         continue;
                     const long long p = g.at(0, m0 + i, f0);
-                    T pv[4], cv[4], qv[4];
-                    load4<T>(prev + p, pv);
-                    load4<T>(a.c0 + p, cv);
-                    load4<T>(a.q + p, qv);
+                    T pv[VW], cv[VW], qv[VW];
+                    loadv(prev + p, pv);
+                    loadv(a.c0 + p, cv);
+                    loadv(a.q + p, qv);
                     if constexpr (Loop2dShape<T, R, VARDEN>::PACKED && MATH == MATH_FAST) {
                         strip_values_packed<R>(a, su, pv, cv, qv, out[i]);
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 4; c++) {
+                        for (int c = 0; c < VW; c++) {
                             const StripNeighbours<T, R, ROWS> nu{su, i, c};
                             const StripNeighbours<T, R, ROWS> nd{VARDEN ? sd : su, i, c};
                             out[i][c] = value_from_neighbours<T, 2, VARDEN, R, MATH>(
@@ -370,26 +396,26 @@ loop2d_persistent_kernel(const __grid_constant__ LoopArgs<T> L)
                     }
                 }
                 // rows / columns clear of every face region: plain vector stores
-                const bool clearF = !a.fuse_bc || (f0 > 2 * R && f0 + 3 < lastF - R);
+                const bool clearF = !a.fuse_bc || (f0 > 2 * R && f0 + VW - 1 < lastF - R);
 #pragma unroll
                 for (int i = 0; i < ROWS; i++) {
                     if (i >= rowsValid)
                         continue;
                     const int m = m0 + i;
                     const bool inBox = L.fuseSources && m >= L.srcLoM && m <= L.srcHiM &&
-                                       f0 + 3 >= L.srcLoF && f0 <= L.srcHiF;
+                                       f0 + VW - 1 >= L.srcLoF && f0 <= L.srcHiF;
                     if (inBox) {
 #pragma unroll
-                        for (int c = 0; c < 4; c++)
+                        for (int c = 0; c < VW; c++)
                             if (c < colsValid)
                                 out[i][c] = loop2d_add_sources<T>(L, n, m, f0 + c, out[i][c]);
                     }
                     const bool clearM = !a.fuse_bc || (m > 2 * R && m < lastM - R);
-                    if (clearF && clearM && colsValid == 4) {
-                        store4(next + g.at(0, m, f0), out[i]);
+                    if (clearF && clearM && colsValid == VW) {
+                        storev(next + g.at(0, m, f0), out[i]);
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 4; c++)
+                        for (int c = 0; c < VW; c++)
                             if (c < colsValid)
                                 simple_store<T, 2>(a, next, 0, m, f0 + c, out[i][c]);
                     }
@@ -455,8 +481,9 @@ static bool launch_loop2d_r(int math, const LoopArgs<T> &L, cudaStream_t stream)
     // no more CTAs than tiles of work; a barrier costs more the wider it is
     const Grid &g = L.a.g;
     constexpr int TILE_ROWS = Loop2dShape<T, R, VARDEN>::TILE_ROWS;
+    constexpr int COLS = Loop2dShape<T, R, VARDEN>::COLS;
     const long long tiles = (long long)((g.nM - 2 * R + TILE_ROWS - 1) / TILE_ROWS) *
-                            ((g.nF - 2 * R + kLoop2dCols - 1) / kLoop2dCols);
+                            ((g.nF - 2 * R + COLS - 1) / COLS);
     long long blocks = (long long)sms * std::min(perSm, 2);
     blocks = std::max<long long>(1, std::min(blocks, tiles));
     void *args[] = {(void *)&L};

@@ -96,7 +96,8 @@ template <typename T, bool VARDEN, int R, int MATH>
 __global__ void __launch_bounds__((Loop2dShape<T, R, VARDEN>::RESIDENT_THREADS), 1)
 loop2d_resident_kernel(const __grid_constant__ LoopArgs<T> L)
 {
-    constexpr int ROWS = Loop2dShape<T, R, VARDEN>::ROWS;
+    // strips of four points (float32); float64 takes the one-point-per-thread path
+    constexpr int ROWS = Loop2dShape<T, R, VARDEN>::VW == 4 ? Loop2dShape<T, R, VARDEN>::ROWS : 0;
     constexpr int RP = (R + 3) / 4 * 4;
     const StepArgs<T> &a = L.a;
     const Grid &g = a.g;
@@ -335,7 +336,8 @@ template <typename T, bool VARDEN, int R>
 static bool resident_tiling_r(int math, const Grid &g, int minTm, int minTf, Loop2dTiling *out)
 {
     constexpr int RP = (R + 3) / 4 * 4;
-    constexpr int ROWS = Loop2dShape<T, R, VARDEN>::ROWS ? Loop2dShape<T, R, VARDEN>::ROWS : 1;
+    constexpr int ROWS = (Loop2dShape<T, R, VARDEN>::VW == 4 && Loop2dShape<T, R, VARDEN>::ROWS)
+                             ? Loop2dShape<T, R, VARDEN>::ROWS : 1;
     auto k = (math == MATH_STRICT) ? loop2d_resident_kernel<T, VARDEN, R, MATH_STRICT>
                                    : loop2d_resident_kernel<T, VARDEN, R, MATH_FAST>;
     int dev = 0, sms = 0, coop = 0, maxSmem = 0;

@@ -44,6 +44,8 @@ def main():
         if mode == "launch":
             os.environ["SIMWAVE_CUDA_LOOP"] = "launch"
         timed(c1, "readme 2D, 512 receivers [%s]" % mode)
+        timed(workloads.marmousi_2d(timesteps=600, dtype=np.float64),
+              "marmousi float64, 1700 receivers [%s]" % mode)
         timed(p, "marmousi, 1700 receivers [%s]" % mode)
         timed(without_receivers(p), "marmousi, 1 receiver [%s]" % mode)
         q = without_receivers(p)

@@ -128,14 +128,15 @@ def marmousi_2d_velocity(seed=1):
     return np.clip(vel, 1028.0, 4700.0).astype(np.float32)
 
 
-def marmousi_2d(space_order=8, timesteps=None, seed=1):
-    """C2: Marmousi-shaped 351 x 1701 model (benchmark/marmousi_2D.py:71-113)."""
+def marmousi_2d(space_order=8, timesteps=None, seed=1, dtype=np.float32):
+    """C2: Marmousi-shaped 351 x 1701 model (benchmark/marmousi_2D.py:71-113;
+    the script itself builds it in float64, ``dtype=np.float64``)."""
     vel = marmousi_2d_velocity(seed)
     return _assemble(
         vel, None, ((0, 70), (70, 70)), (10.0, 10.0), space_order,
         ("null_neumann", "null_dirichlet", "null_dirichlet", "null_dirichlet"),
         [(20.0, 8500.0)], [(20.0, 10.0 * i) for i in range(1700)],
-        1, 10.0, 2.0, timesteps, name="marmousi_2d")
+        1, 10.0, 2.0, timesteps, dtype=dtype, name="marmousi_2d")
 
 
 def _layered_3d(shape, vmin, vmax, seed, step_axis=2):

@@ -392,10 +392,17 @@ int simwave_cuda_last_loop_kind(void);
 
 /* Device buffers and pinned staging buffers are kept between calls (a survey
  * calls forward() once per shot with the same shapes); this hands every cached
- * block back to the driver.  The cache is bounded by half of the device memory
- * and 512 MiB of pinned memory, is emptied automatically when an allocation
- * fails, and is off altogether with SIMWAVE_CUDA_CACHE=0. */
+ * block back to the driver.  The cache holds the working set of the last
+ * forward() only (see simwave_cuda_cached_bytes), is bounded by half of the
+ * device memory and 512 MiB of pinned memory, is emptied automatically when an
+ * allocation fails, and is off altogether with SIMWAVE_CUDA_CACHE=0. */
 void simwave_cuda_release_cache(void);
+
+/* Device memory the cache holds right now, in bytes, over all devices.  After
+ * a forward() this is the working set of that call and nothing older: blocks
+ * an earlier call left behind and this one did not take again are freed when
+ * it returns (SIMWAVE_CUDA_CACHE=keep keeps everything, =0 nothing). */
+unsigned long long simwave_cuda_cached_bytes(void);
 
 /*
  * Hints: promises of the caller about the next forward() calls on this thread

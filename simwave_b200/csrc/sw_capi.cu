@@ -582,6 +582,8 @@ int simwave_cuda_set_slab_devices(const int *devices, int count)
     return 0;
 }
 
+unsigned long long simwave_cuda_cached_bytes(void) { return sw::cached_device_bytes(); }
+
 void simwave_cuda_release_cache(void)
 {
     sw::drop_resident_models();

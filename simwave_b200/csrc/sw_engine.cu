@@ -272,6 +272,16 @@ void cache_end_call()
     cudaGetLastError();
 }
 
+size_t cached_device_bytes()
+{
+    Caches &c = caches();
+    std::lock_guard<std::mutex> lk(c.mu);
+    size_t total = 0;
+    for (auto &kv : c.deviceBytes)
+        total += kv.second;
+    return total;
+}
+
 void cache_mark_exported(void *base)
 {
     Caches &c = caches();

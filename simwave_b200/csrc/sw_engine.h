@@ -83,6 +83,7 @@ void release_caches();
 // used and nothing older (SIMWAVE_CUDA_CACHE=keep turns the trimming off)
 void cache_begin_call();
 void cache_end_call();
+size_t cached_device_bytes();       // device memory held by the cache, all devices
 
 // true if [p, p+1) is page-locked host memory known to the CUDA driver
 bool is_pinned_host(const void *p);

@@ -104,3 +104,24 @@ def test_cuda_arm_imports_nothing_from_the_oracle():
         with open(os.path.join(REPO, "tests", name)) as f:
             text = f.read()
         assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), name
+
+
+def test_cpu_baseline_runs_in_a_child_and_leaves_the_gpu_arm_unbound():
+    """The GPU arm must not export OMP_PROC_BIND: libgomp would pin the main
+    thread to one core at `import torch` and every helper thread of the CUDA
+    library would inherit that mask.  Its cpu_baseline comes from a child
+    process (`bench.py --cpu-child`), which does bind its OpenMP threads."""
+    probe = ("import sys, os; sys.argv = ['bench.py']; sys.path.insert(0, %r); "
+             "import bench; print(os.environ.get('OMP_PROC_BIND'), "
+             "len(os.sched_getaffinity(0)) == bench.host_threads())" % REPO)
+    env = {k: v for k, v in os.environ.items() if not k.startswith("OMP_")}
+    out = subprocess.run([sys.executable, "-c", probe], cwd=REPO, env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.split() == ["None", "True"]
+
+    child = _run([sys.executable, "bench.py", "--cpu-child", "--workload", "readme_2d",
+                  "--cpu-timesteps", "4"])
+    assert child.returncode == 0, child.stderr[-2000:]
+    (line,) = _json_lines(child.stdout)
+    assert line["seconds"] > 0 and line["kind"] in ("ref", "port") and line["threads"] >= 1

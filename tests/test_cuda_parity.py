@@ -592,6 +592,27 @@ def test_pinned_and_pageable_host_buffers_agree():
     assert np.array_equal(pageable["receivers"], pinned["receivers"])
 
 
+def test_allocation_cache_keeps_the_last_working_set_only():
+    """A survey over changing shapes must not pile up dead device blocks: after
+    a forward() the cache holds what that call used, nothing an earlier,
+    larger problem left behind."""
+    lib = core()
+    lib.simwave_cuda_cached_bytes.restype = ctypes.c_ulonglong
+    lib.simwave_cuda_release_cache()
+    big = problems.make_problem(shape=(60, 200, 210), space_order=8, timesteps=3, seed=1)
+    small = problems.make_problem(shape=(30, 64, 70), space_order=8, timesteps=3, seed=1)
+    cuda_forward(big)
+    after_big = lib.simwave_cuda_cached_bytes()
+    assert after_big >= 5 * big["velocity"].nbytes        # fields of the big problem are kept
+    cuda_forward(small)
+    after_small = lib.simwave_cuda_cached_bytes()
+    assert 0 < after_small < big["velocity"].nbytes        # ... and gone after a smaller call
+    cuda_forward(small)
+    assert lib.simwave_cuda_cached_bytes() == after_small  # steady state of a survey
+    lib.simwave_cuda_release_cache()
+    assert lib.simwave_cuda_cached_bytes() == 0
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("density", [False, True])
 @pytest.mark.parametrize("order", [2, 4, 6, 8, 10, 12, 14, 16, 20])

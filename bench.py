@@ -785,6 +785,18 @@ def run_ours(args, p, rank, world, local_rank):
             cpu = {"value": None, "unit": "Gpts/s", "cores": host_threads(),
                    "kind": "port", "sample": "failed: %s" % e}
 
+    # ---- C5: multi-shot survey through forward() ------------------------------
+    # (before the slab legs: their model generation on the GPU and their peer
+    # mappings leave state behind that a survey process would not have)
+    survey = None
+    if args.shots > 0 and not args.no_survey:
+        try:
+            survey = run_survey_leg(args, rank, world, barrier, max_over_ranks)
+        except Exception as e:
+            if world > 1:
+                raise
+            survey = {"error": "%s: %s" % (type(e).__name__, e)}
+
     # ---- slab decomposition legs (C4-shaped) ---------------------------------
     slab_result = slab_strong = None
     if not args.no_slab:
@@ -799,16 +811,6 @@ def run_ours(args, p, rank, world, local_rank):
             if world > 1:
                 raise               # ranks wait on each other: fail together
             slab_result = {"error": "%s: %s" % (type(e).__name__, e)}
-
-    # ---- C5: multi-shot survey through forward() ------------------------------
-    survey = None
-    if args.shots > 0 and not args.no_survey:
-        try:
-            survey = run_survey_leg(args, rank, world, barrier, max_over_ranks)
-        except Exception as e:
-            if world > 1:
-                raise
-            survey = {"error": "%s: %s" % (type(e).__name__, e)}
 
     # ---- C1 / C2: the 2D configurations (N == 1) -------------------------------
     configs_2d = None

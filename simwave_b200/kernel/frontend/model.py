@@ -330,14 +330,42 @@ class SpaceModel:
         (reference model.py:378-406).  Read-only; kept between accesses.
         """
         def build():
-            mask = np.pad(
-                array=np.zeros(self.shape, dtype=self.dtype),
-                pad_width=self.nbl_pad_width,
+            # The reference pads a zero array of the whole grid with linear
+            # ramps, axis after axis, then raises it to the degree: several
+            # passes over 10^9 points for a 1024^3 model.  A ramp value only
+            # depends on how deep the point sits in the layer of every axis
+            # (numpy ramps from the end value to the EDGE value, which itself
+            # only depends on the depths along the axes padded before), not
+            # on the size of the physical domain.  So the same numpy calls on
+            # a ONE-cell domain give every distinct value, bit for bit, and
+            # the full mask is a gather from that small array.
+            widths = self.nbl_pad_width
+            small = np.pad(
+                array=np.zeros((1,) * self.dimension, dtype=self.dtype),
+                pad_width=widths,
                 mode="linear_ramp",
-                end_values=self.nbl_pad_width
+                end_values=widths
             )
-            mask = (mask ** self.damping_polynomial_degree) * self.damping_alpha
-            return np.pad(array=mask, pad_width=self.halo_pad_width)
+            small = (small ** self.damping_polynomial_degree) * self.damping_alpha
+            # index into `small` of every grid index along each axis
+            index = []
+            for n, (before, after) in zip(self.shape, widths):
+                i = np.full(before + n + after, before, dtype=np.intp)
+                i[:before] = np.arange(before)
+                i[before + n:] = before + 1 + np.arange(after)
+                index.append(i)
+            halo = self.halo_pad_width
+            shape = tuple(len(i) + hb + ha for i, (hb, ha) in zip(index, halo))
+            mask = np.zeros(shape, dtype=small.dtype)
+            core = mask[tuple(slice(hb, s - ha) for s, (hb, ha) in zip(shape, halo))]
+            # slowest axis: every index of the physical domain shares one
+            # hyperplane, the layer indices have their own
+            rest = np.ix_(*index[1:]) if self.dimension > 1 else ()
+            before0, n0 = widths[0][0], self.shape[0]
+            core[before0:before0 + n0] = small[(before0,) + rest]
+            for k in list(range(before0)) + list(range(before0 + n0, len(index[0]))):
+                core[k] = small[(index[0][k],) + rest]
+            return mask
         return self._kept('damping_mask', build)
 
     @property

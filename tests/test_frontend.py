@@ -197,3 +197,34 @@ def test_middleware_withdraws_its_hints_after_the_call():
     Middleware._apply_hints(lib, dict.fromkeys(done, 0))
     assert lib.simwave_cuda_set_hint.calls == [(1, 1), (3, 42), (1, 0), (3, 0)]
     assert Middleware._apply_hints(object(), {'wavefield_out': 1}) == []
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_damping_mask_equals_the_reference_procedure(seed):
+    """SpaceModel.damping_mask gathers from the mask of a one-cell domain (the
+    ramp values only depend on the depth inside the layers); it must equal,
+    bit for bit, what the reference computes over the whole grid
+    (model.py:378-406: np.pad linear_ramp, power, alpha, halo padding)."""
+    rng = np.random.default_rng(seed)
+    dim = 2 + seed % 2
+    shape = tuple(int(x) for x in rng.integers(3, 28, size=dim))
+    dtype = (np.float32, np.float64)[seed % 2 if seed > 1 else seed]
+    h = tuple(float(x) for x in rng.uniform(5, 20, size=dim))
+    box = []
+    for n, hh in zip(shape, h):
+        box += [0.0, (n - 1) * hh]
+    sm = api.SpaceModel(bounding_box=tuple(box), grid_spacing=h,
+                        velocity_model=rng.uniform(1500, 3000, size=shape).astype(dtype),
+                        space_order=int(rng.choice([2, 4, 8, 16])), dtype=dtype)
+    lengths = tuple(float(rng.integers(0, 12)) * hh for hh in h for _ in range(2))
+    sm.config_boundary(damping_length=lengths,
+                       boundary_condition=("null_neumann",) * (2 * dim),
+                       damping_polynomial_degree=int(rng.integers(1, 5)),
+                       damping_alpha=float(rng.uniform(1e-4, 1e-2)))
+    want = np.pad(array=np.zeros(sm.shape, dtype=sm.dtype), pad_width=sm.nbl_pad_width,
+                  mode="linear_ramp", end_values=sm.nbl_pad_width)
+    want = (want ** sm.damping_polynomial_degree) * sm.damping_alpha
+    want = np.pad(array=want, pad_width=sm.halo_pad_width)
+    got = sm.damping_mask
+    assert got.dtype == want.dtype and got.shape == want.shape
+    assert np.array_equal(got, want)

@@ -231,3 +231,34 @@ def test_c4_full_size_equals_the_oracle_inside_the_cone_and_is_zero_outside(c4, 
     cuda_forward(two)
     assert_doubled(two["receivers"], full["receivers"])
     assert_doubled(two["u"][1], full["u"][1])
+
+
+@pytest.mark.parametrize("name", ["readme_2d", "marmousi_2d"])
+def test_2d_configurations_whole_run_against_the_oracle(name, monkeypatch):
+    """C1 and C2 are small enough for the CPU oracle to run them whole (328 and
+    1696 time steps): strict mode bit for bit, the default mode within the
+    stated tolerance of a long loop."""
+    p = workloads.WORKLOADS[name]()
+    ref = fresh(p)
+    # the reference's OpenMP build of the same kernel: with one source it is
+    # bit-identical to the sequential build (checked on a prefix of the run)
+    # and finishes the 1696 steps of C2 in seconds
+    variant = "omp" if oracle.available("ref", 2, False, np.float32, "omp") else ""
+    if variant:
+        a, b = fresh(p), fresh(p)
+        a["end_timestep"] = b["end_timestep"] = 40
+        oracle.forward(a)
+        oracle.forward(b, variant=variant)
+        assert np.array_equal(a["u"], b["u"]) and np.array_equal(a["receivers"], b["receivers"])
+    oracle.forward(ref, variant=variant)
+    assert np.abs(ref["receivers"]).max() > 0
+    monkeypatch.setenv("SIMWAVE_CUDA_MATH", "strict")
+    strict = fresh(p)
+    cuda_forward(strict)
+    assert np.array_equal(strict["u"], ref["u"])
+    assert np.array_equal(strict["receivers"], ref["receivers"])
+    monkeypatch.setenv("SIMWAVE_CUDA_MATH", "fast")
+    fast = fresh(p)
+    cuda_forward(fast)
+    assert rel_l2(fast["u"], ref["u"]) <= 1e-4
+    assert rel_l2(fast["receivers"], ref["receivers"]) <= 1e-4

@@ -262,3 +262,37 @@ def test_2d_configurations_whole_run_against_the_oracle(name, monkeypatch):
     cuda_forward(fast)
     assert rel_l2(fast["u"], ref["u"]) <= 1e-4
     assert rel_l2(fast["receivers"], ref["receivers"]) <= 1e-4
+
+
+def test_c5_survey_shots_on_a_resident_model_against_the_oracle(monkeypatch):
+    """C5 as bench.py drives it: one 512^3 model kept on the device under a
+    caller token, every shot a drop-in forward() with the data-path hints on
+    (zero wavefield in, traces only out).  The traces of three shots -- the
+    second and third find the model of the first on the device -- against the
+    CPU oracle on the sub-volume each shot can have reached."""
+    import ctypes
+    from cuda_abi import core
+    lib = core()
+    lib.simwave_cuda_set_hint.argtypes = [ctypes.c_int, ctypes.c_longlong]
+    T = 12
+    base = workloads.shot_3d(shot=0, timesteps=T)
+    base["wavelet"] = lively_wavelet(base, 3)
+    monkeypatch.setenv("SIMWAVE_CUDA_MATH", "fast")
+    try:
+        for hint, value in ((1, 1), (2, 2), (3, 4242)):
+            assert lib.simwave_cuda_set_hint(hint, value) == 0
+        for shot in (0, 5, 63):
+            p = workloads.reshoot(base, shot)
+            cuda_forward(p)
+            assert not p["u"].any()                      # nothing but the traces comes back
+            small, box, keep = crop_around_sources(p, T, 14)
+            assert len(keep) > 8
+            oracle.forward(small)
+            assert np.abs(small["receivers"]).max() > 0
+            assert rel_l2(p["receivers"][:, keep], small["receivers"]) <= 1e-5
+            others = np.setdiff1d(np.arange(p["receivers"].shape[1]), keep)
+            assert not p["receivers"][:, others].any()
+    finally:
+        for hint in (1, 2, 3):
+            lib.simwave_cuda_set_hint(hint, 0)
+        lib.simwave_cuda_release_cache()

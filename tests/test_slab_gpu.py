@@ -106,6 +106,28 @@ def test_slabs_on_one_device_equal_the_single_plan_run(shape, order, density, st
     assert rel_l2(traces, cpu["receivers"]) <= 1e-5
 
 
+@pytest.mark.parametrize("math,push", [("strict", "fused"), ("fast", "fused"),
+                                       ("fast", "copy")])
+def test_float64_slabs_equal_the_single_plan_run(math, push, tmp_path, monkeypatch):
+    """The float64 tiled kernel (sw_step_tiled3d64.cuh) under slab
+    decomposition: its ghost-plane stores, fused and copy push, two slabs."""
+    shape, order, world = (84, 58, 70), 8, 2
+    cuts = [lo for lo, _ in slab.split_planes(shape[0], order // 2, world)][1:]
+    kwargs = problem_kwargs(shape, order, False, 18, (2, 1, 2, 1, 0, 2), cuts)
+    kwargs["dtype"] = "float64"
+    case = {"math": math, "push": push, "problem": kwargs, "passes": 1}
+    parts, infos, traces = run_slabs(case, world, tmp_path)
+    u = slab.assemble_wavefield(parts, infos, shape[0])
+    monkeypatch.setenv("SIMWAVE_CUDA_MATH", math)
+    p = problems.make_problem(**kwargs)
+    assert p["u"].dtype == np.float64
+    single = problems.clone(p)
+    cuda_forward(single)
+    assert np.abs(single["u"]).max() > 0
+    assert np.array_equal(u, single["u"])
+    assert rel_l2(traces, single["receivers"]) <= 1e-12
+
+
 def _device_count():
     from cuda_abi import core
     return core().simwave_cuda_device_count()

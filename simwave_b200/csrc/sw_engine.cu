@@ -1394,10 +1394,68 @@ void Plan<T>::choose_tiling()
                 }
         }
         int zchunk = 0;
-        if (const char *e = std::getenv("SIMWAVE_CUDA_TILE")) {
-            cfg = std::atoi(e);
-            if (const char *c = std::strchr(e, ':'))
+        const char *tileEnv = std::getenv("SIMWAVE_CUDA_TILE");
+        if (tileEnv) {
+            cfg = std::atoi(tileEnv);
+            if (const char *c = std::strchr(tileEnv, ':'))
                 zchunk = std::atoi(c + 1);
+        }
+
+        // How a configuration would split S into chunks on this grid: the CTAs
+        // should fill whole waves (a wave = SMs x resident CTAs), against the
+        // cost of a chunk's 2r priming planes of u_cur (re-read by the
+        // neighbouring chunk).  Returns the number of chunks; *score rates the
+        // configuration: wave fill x priming overhead / bytes a point moves
+        // between L2 and the SMs (the halo of the u_cur tile included).
+        int sms = 148, maxSmemSm = 0;
+        SW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_));
+        SW_CUDA(cudaDeviceGetAttribute(&maxSmemSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor,
+                                       device_));
+        const int interior = g_.nS - 2 * r;
+        auto chunking = [&](const TiledInfo &info, double *score) {
+            const long long tF = (g_.nF - 2 * r + info.tileF() - 1) / info.tileF();
+            const long long tM = (g_.nM - 2 * r + info.tileM() - 1) / info.tileM();
+            const int threads = info.tx * info.ty + 32;
+            int resident = std::max(1, std::min(maxSmemSm / (info.smemBytes + 1024),
+                                                2048 / threads));
+            resident = std::min(resident, info.minBlocks);
+            const double slots = (double)sms * resident;
+            const double haloBytes = (double)sizeof(T) * (info.tileM() + 2 * r) *
+                                     (info.tileF() + 2 * halo_f(r)) /
+                                     ((double)info.tileM() * info.tileF());
+            const double alg = (varden_ ? 36.0 : 20.0) * sizeof(T) / 4;
+            double best = -1;
+            int bestChunks = 1;
+            for (int chunks = 1; chunks <= 64 && interior / chunks >= 2 * r; chunks++) {
+                const int len = (interior + chunks - 1) / chunks;
+                const int real = (interior + len - 1) / len;
+                const double waves = tF * tM * real / slots;
+                const double fill = waves / std::ceil(waves);
+                const double traffic = alg / (alg + 2.0 * r * haloBytes / len);
+                const double sc = fill * traffic;
+                if (sc > best + 1e-9) { best = sc; bestChunks = chunks; }
+            }
+            if (score)
+                *score = best / (alg - sizeof(T) + haloBytes);
+            return bestChunks;
+        };
+
+        // float32, constant density, r <= 5: the 14 x 64 tile (two CTAs per SM)
+        // or the 30 x 64 tile (one CTA of 16 warps: a fifth less halo traffic,
+        // which is what counts once a long loop runs under the power cap --
+        // C3 over 2651 steps: 286 against 273 Gpts/s; 512^3 shots: 329 against
+        // 301 -- while short bursts on C3 prefer the small tile, 300 against
+        // 286), whichever rates higher on this grid
+        if (kF32 && !varden_ && r <= 5 && !tileEnv) {
+            double bestScore = -1;
+            for (int c : {0, 7}) {
+                TiledInfo info{};
+                double sc = 0;
+                if (!kTiledQuery[r](c, varden_, opt_.math, &info) || info.smemBytes > maxSmem)
+                    continue;
+                chunking(info, &sc);
+                if (sc > bestScore) { bestScore = sc; cfg = c; }
+            }
         }
         if (kF32) {
             if (!kTiledQuery[r](cfg, varden_, opt_.math, &tiledInfo_))
@@ -1409,39 +1467,11 @@ void Plan<T>::choose_tiling()
         if (tiledInfo_.smemBytes > maxSmem)
             return;   // plain kernel
         tiledCfg_ = cfg;
-        const int interior = g_.nS - 2 * r;
         const long long tilesF = (g_.nF - 2 * r + tiledInfo_.tileF() - 1) / tiledInfo_.tileF();
         const long long tilesM = (g_.nM - 2 * r + tiledInfo_.tileM() - 1) / tiledInfo_.tileM();
         if (zchunk <= 0) {
-            // Split S into chunks so that the CTAs fill whole waves (a wave =
-            // SMs x resident CTAs), against the cost of a chunk's 2r priming
-            // planes of u_cur (re-read by the neighbouring chunk).
-            int sms = 148;
-            SW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_));
-            int maxSmemSm = 0;
-            SW_CUDA(cudaDeviceGetAttribute(&maxSmemSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor,
-                                           device_));
-            const int threads = tiledInfo_.tx * tiledInfo_.ty + 32;
-            int resident = std::max(1, std::min(maxSmemSm / (tiledInfo_.smemBytes + 1024),
-                                                2048 / threads));
-            resident = std::min(resident, tiledInfo_.minBlocks);
-            const double slots = (double)sms * resident;
-            const double haloBytes = (double)sizeof(T) * (tiledInfo_.tileM() + 2 * r) *
-                                     (tiledInfo_.tileF() + 2 * halo_f(r)) /
-                                     ((double)tiledInfo_.tileM() * tiledInfo_.tileF());
-            double best = -1;
-            int bestChunks = 1;
-            for (int chunks = 1; chunks <= 64 && interior / chunks >= 2 * r; chunks++) {
-                const int len = (interior + chunks - 1) / chunks;
-                const int real = (interior + len - 1) / len;
-                const double waves = tilesF * tilesM * real / slots;
-                const double fill = waves / std::ceil(waves);
-                const double alg = (varden_ ? 36.0 : 20.0) * sizeof(T) / 4;
-                const double traffic = alg / (alg + 2.0 * r * haloBytes / len);
-                const double score = fill * traffic;
-                if (score > best + 1e-9) { best = score; bestChunks = chunks; }
-            }
-            zchunk = (interior + bestChunks - 1) / bestChunks;
+            const int chunks = chunking(tiledInfo_, nullptr);
+            zchunk = (interior + chunks - 1) / chunks;
         }
         zChunk_ = std::max(1, std::min(zchunk, interior));
         useTiled_ = true;

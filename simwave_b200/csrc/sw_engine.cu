@@ -1446,16 +1446,20 @@ void Plan<T>::choose_tiling()
         // C3 over 2651 steps: 286 against 273 Gpts/s; 512^3 shots: 329 against
         // 301 -- while short bursts on C3 prefer the small tile, 300 against
         // 286), whichever rates higher on this grid
-        if (kF32 && !varden_ && r <= 5 && !tileEnv) {
-            double bestScore = -1;
-            for (int c : {0, 7}) {
+        // Variable density, r <= 5: likewise the 22 x 64 tile (one CTA of 12
+        // warps, three stream stages) against the 16 x 64 tile (two CTAs); the
+        // large tile measured 195 against 178 Gpts/s on a 512^3 so-8 model and
+        // wins a near tie (profiles/r02_sweep_vd_so8_sustained.txt).
+        if (kF32 && r <= 5 && !tileEnv) {
+            const int large = varden_ ? 3 : 7;
+            double score[2] = {-1, -1};
+            const int cand[2] = {0, large};
+            for (int i = 0; i < 2; i++) {
                 TiledInfo info{};
-                double sc = 0;
-                if (!kTiledQuery[r](c, varden_, opt_.math, &info) || info.smemBytes > maxSmem)
-                    continue;
-                chunking(info, &sc);
-                if (sc > bestScore) { bestScore = sc; cfg = c; }
+                if (kTiledQuery[r](cand[i], varden_, opt_.math, &info) && info.smemBytes <= maxSmem)
+                    chunking(info, &score[i]);
             }
+            cfg = (score[1] >= (varden_ ? 0.97 : 1.0) * score[0]) ? large : 0;
         }
         if (kF32) {
             if (!kTiledQuery[r](cfg, varden_, opt_.math, &tiledInfo_))

@@ -238,3 +238,26 @@ def test_source_errors_and_wavelets():
     assert multi.num_sources == 3 and multi.values.flags["C_CONTIGUOUS"]
     with pytest.raises(ValueError):
         MultiWavelet(np.ones((time.timesteps + 1, 3)), time)
+
+
+def test_every_environment_knob_is_documented():
+    """Every SIMWAVE_* variable the sources read is described in
+    INTEGRATION.md or in include/simwave_cuda.h."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sources = glob.glob(os.path.join(root, "simwave_b200", "csrc", "*.c*")) + \
+        glob.glob(os.path.join(root, "simwave_b200", "csrc", "*.h")) + \
+        glob.glob(os.path.join(root, "simwave_b200", "**", "*.py"), recursive=True)
+    names = set()
+    for path in sources:
+        with open(path) as f:
+            names.update(re.findall(r"SIMWAVE_(?:CUDA|B200)_[A-Z0-9_]+", f.read()))
+    names = {n for n in names if not n.endswith("_")}     # macro prefixes
+    docs = ""
+    for path in ("INTEGRATION.md", os.path.join("include", "simwave_cuda.h")):
+        with open(os.path.join(root, path)) as f:
+            docs += f.read()
+    missing = sorted(n for n in names if n not in docs)
+    assert not missing, missing
